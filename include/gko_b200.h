@@ -1,0 +1,219 @@
+/* gko_b200.h — C-ABI of libgko_b200.so: Blackwell (sm_100a) kernels for Ginkgo's
+ * sparse-solve hot path.
+ *
+ * This is the drop-in boundary.  Every entry point below replaces one kernel of
+ * the reference's `gko::kernels::cuda::<area>::<kernel>` namespace (the functions
+ * `libginkgo_cuda.so` exports and `Executor::run` dispatches to,
+ * include/ginkgo/core/base/executor.hpp:456-510), or one host-side solver loop
+ * (core/solver/{cg,bicgstab,gmres}.cpp) that we re-issue as a fused, graph-captured
+ * sequence.  The reference declaration each function stands in for is cited as
+ * `[ref: file:line]`, paths relative to the Ginkgo 1.5.0 tree.  INTEGRATION.md shows
+ * the C++ shim a Ginkgo maintainer adds to bind them.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++/torch types cross this boundary.
+ *  - all array pointers are DEVICE pointers unless the parameter name ends in
+ *    `_host`.  Scalars alpha/beta/rho/... are device-resident (Ginkgo passes them as
+ *    1x1 / 1xk Dense on the executor).
+ *  - `stream` is a cudaStream_t passed as void*.  Calls enqueue work and return;
+ *    they never synchronise, never allocate and never free (the `*_create`,
+ *    `*_destroy`, `*_generate` setup calls and functions documented "blocking" excepted).
+ *  - return value: 0 on success, a positive cudaError_t on CUDA failure, or one of
+ *    the negative GKOB200_E* codes.  Empty inputs are successful no-ops
+ *    [ref: cuda/matrix/csr_kernels.cu:435-436].
+ *  - dense vectors/multivectors are row-major, element (i,j) at v[i*stride + j]
+ *    [ref: include/ginkgo/core/matrix/dense.hpp:685,1173].
+ *  - suffixes: _f64/_f32 = ValueType double/float, _i32/_i64 = IndexType.
+ *  - there is NO CPU fallback anywhere in this library.
+ */
+#ifndef GKO_B200_H_
+#define GKO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GKOB200_EINVAL (-1)     /* bad argument (null pointer, negative size, ...) */
+#define GKOB200_EUNSUPPORTED (-2) /* combination not implemented on this path */
+#define GKOB200_EWORKSPACE (-3) /* caller-provided workspace too small */
+#define GKOB200_ENOTCONVERGED (-4)
+
+/* Bytes of zero-initialised device scratch every reducing kernel needs
+ * (ticket + per-block partial sums).  Initialise once with
+ * gkob200_reduce_ws_init; kernels leave it re-armed. */
+#define GKOB200_REDUCE_WS_BYTES (256 + 148 * 16 * 8 * 8)
+
+int gkob200_version(void);
+/* Number of SMs of the current device (blocking, cached). */
+int gkob200_sm_count(void);
+int gkob200_reduce_ws_init(void* stream, void* ws);
+
+/* ------------------------------------------------------------------------- *
+ * CSR SpMV / SpMM
+ * [ref: core/matrix/csr_kernels.hpp:59-70  csr::spmv, csr::advanced_spmv;
+ *       oracle reference/matrix/csr_kernels.cpp:75-129;
+ *       replaced cuda/matrix/csr_kernels.cu:430-542]
+ * c = A b                      (alpha == NULL && beta == NULL)
+ * c = alpha * A b + beta * c   (both non-NULL, device scalars)
+ * strategy: which kernel runs (the reference switches on the strategy NAME per call,
+ * cuda/matrix/csr_kernels.cu:431-479; here the choice is made once from row-length
+ * statistics, see gkob200_csr_row_stats_* / gkob200_csr_pick_strategy).
+ * ------------------------------------------------------------------------- */
+enum gkob200_csr_strategy {
+    GKOB200_CSR_CLASSICAL = 0,  /* row-block kernel: coalesced streams staged in shared
+                                   memory, one thread per row, oracle summation order
+                                   (bit-identical to the reference executor)          */
+    GKOB200_CSR_MERGE_PATH = 1, /* load-balanced merge-path kernel (skewed rows)      */
+    GKOB200_CSR_AUTO = 2        /* = pick_strategy() when stats are given, else MERGE  */
+};
+
+/* Row-length statistics of a CSR matrix (device kernel, result on device):
+ * stats[0] = max row nnz, stats[1] = max nnz of any block of 128 consecutive rows,
+ * stats[2] = number of empty rows, stats[3] = nnz.  int64 each.
+ * [ref: include/ginkgo/core/matrix/csr.hpp:242-262 classical::process computes the max
+ * row length on the host after a D2H copy of row_ptrs] */
+int gkob200_csr_row_stats_i32(void* stream, int64_t n_rows, const int32_t* row_ptrs, int64_t* stats);
+int gkob200_csr_row_stats_i64(void* stream, int64_t n_rows, const int64_t* row_ptrs, int64_t* stats);
+/* Host-side decision from those statistics (pure function, no CUDA). */
+int gkob200_csr_pick_strategy(int64_t n_rows, int64_t nnz, int64_t max_row_nnz, int64_t max_block_nnz);
+
+#define GKOB200_DECL_CSR_SPMV(V, VT, I, IT)                                                   \
+    int gkob200_csr_spmv_##V##_##I(void* stream, int64_t n_rows, int64_t n_cols, int64_t nnz, \
+                                   const IT* row_ptrs, const IT* col_idxs, const VT* values,  \
+                                   const VT* b, int64_t b_stride, int64_t nrhs,               \
+                                   const VT* alpha, const VT* beta, VT* c, int64_t c_stride,  \
+                                   int strategy, int64_t max_block_nnz, void* workspace,      \
+                                   size_t workspace_bytes);
+GKOB200_DECL_CSR_SPMV(f64, double, i32, int32_t)
+GKOB200_DECL_CSR_SPMV(f32, float, i32, int32_t)
+GKOB200_DECL_CSR_SPMV(f64, double, i64, int64_t)
+GKOB200_DECL_CSR_SPMV(f32, float, i64, int64_t)
+/* Workspace the merge-path kernel needs for its per-tile carries (bytes). */
+size_t gkob200_csr_spmv_workspace_bytes(int64_t n_rows, int64_t nnz, int64_t nrhs, int value_bytes);
+
+/* ------------------------------------------------------------------------- *
+ * Dense BLAS-1  [ref: core/matrix/dense_kernels.hpp; oracle
+ * reference/matrix/dense_kernels.cpp:158-378; replaced
+ * common/unified/matrix/dense_kernels.cpp:58-466 + cuda/matrix/dense_kernels.cu:76-149]
+ * x, y: n x k row-major.  `alpha` is 1x1 (alpha_cols==1) or 1xk (alpha_cols==k).
+ * result: 1 x k on device.  ws: GKOB200_REDUCE_WS_BYTES of initialised scratch.
+ * ------------------------------------------------------------------------- */
+#define GKOB200_DECL_DENSE(V, VT)                                                                        \
+    int gkob200_dense_fill_##V(void* stream, int64_t n, int64_t k, VT* x, int64_t stride, VT value);    \
+    int gkob200_dense_copy_##V(void* stream, int64_t n, int64_t k, const VT* x, int64_t xs, VT* y,      \
+                               int64_t ys);                                                              \
+    int gkob200_dense_scale_##V(void* stream, int64_t n, int64_t k, const VT* alpha, int64_t alpha_cols, \
+                                VT* x, int64_t xs);                                                      \
+    int gkob200_dense_inv_scale_##V(void* stream, int64_t n, int64_t k, const VT* alpha,                 \
+                                    int64_t alpha_cols, VT* x, int64_t xs);                              \
+    int gkob200_dense_add_scaled_##V(void* stream, int64_t n, int64_t k, const VT* alpha,                \
+                                     int64_t alpha_cols, const VT* x, int64_t xs, VT* y, int64_t ys);    \
+    int gkob200_dense_sub_scaled_##V(void* stream, int64_t n, int64_t k, const VT* alpha,                \
+                                     int64_t alpha_cols, const VT* x, int64_t xs, VT* y, int64_t ys);    \
+    int gkob200_dense_compute_dot_##V(void* stream, int64_t n, int64_t k, const VT* x, int64_t xs,       \
+                                      const VT* y, int64_t ys, VT* result, void* ws);                    \
+    int gkob200_dense_compute_norm2_##V(void* stream, int64_t n, int64_t k, const VT* x, int64_t xs,     \
+                                        VT* result, void* ws);                                           \
+    int gkob200_dense_compute_squared_norm2_##V(void* stream, int64_t n, int64_t k, const VT* x,         \
+                                                int64_t xs, VT* result, void* ws);                       \
+    int gkob200_dense_compute_norm1_##V(void* stream, int64_t n, int64_t k, const VT* x, int64_t xs,     \
+                                        VT* result, void* ws);                                           \
+    int gkob200_dense_compute_sqrt_##V(void* stream, int64_t k, VT* x);                                  \
+    int gkob200_dense_row_gather_##V##_i32(void* stream, int64_t n_out, int64_t k, const int32_t* rows,  \
+                                           const VT* src, int64_t ss, VT* dst, int64_t ds);              \
+    int gkob200_dense_row_gather_##V##_i64(void* stream, int64_t n_out, int64_t k, const int64_t* rows,  \
+                                           const VT* src, int64_t ss, VT* dst, int64_t ds);
+GKOB200_DECL_DENSE(f64, double)
+GKOB200_DECL_DENSE(f32, float)
+
+/* ------------------------------------------------------------------------- *
+ * CG step kernels, 1:1 with the reference kernel set
+ * [ref: core/solver/cg_kernels.hpp:55-79; oracle reference/solver/cg_kernels.cpp:56-133;
+ *       replaced common/unified/solver/cg_kernels.cpp:51-138]
+ * All vectors n x k with the same `stride`; scalars 1 x k; stop_status k bytes.
+ * ------------------------------------------------------------------------- */
+#define GKOB200_DECL_CG(V, VT)                                                                     \
+    int gkob200_cg_initialize_##V(void* stream, int64_t n, int64_t k, const VT* b, int64_t b_stride, \
+                                  VT* r, VT* z, VT* p, VT* q, int64_t stride, VT* prev_rho, VT* rho, \
+                                  uint8_t* stop_status);                                            \
+    int gkob200_cg_step_1_##V(void* stream, int64_t n, int64_t k, VT* p, const VT* z, int64_t stride, \
+                              const VT* rho, const VT* prev_rho, const uint8_t* stop_status);       \
+    int gkob200_cg_step_2_##V(void* stream, int64_t n, int64_t k, VT* x, int64_t x_stride, VT* r,   \
+                              const VT* p, const VT* q, int64_t stride, const VT* beta,             \
+                              const VT* rho, const uint8_t* stop_status);
+GKOB200_DECL_CG(f64, double)
+GKOB200_DECL_CG(f32, float)
+
+/* ------------------------------------------------------------------------- *
+ * Stopping criteria  [ref: core/stop/residual_norm_kernels.hpp:49-80; oracle
+ * reference/stop/residual_norm_kernels.cpp:58-137; replaced
+ * cuda/stop/residual_norm_kernels.cu:61-199 which ends in two blocking 1-byte D2H
+ * copies per call].  Here the two booleans are written to `flags` (device or
+ * pinned-mapped host memory): flags[0] = all_converged, flags[1] = one_changed.
+ * ------------------------------------------------------------------------- */
+#define GKOB200_DECL_STOP(V, VT)                                                                   \
+    int gkob200_residual_norm_##V(void* stream, int64_t k, const VT* tau, const VT* orig_tau,      \
+                                  VT rel_residual_goal, uint8_t stopping_id, int set_finalized,    \
+                                  uint8_t* stop_status, uint8_t* flags);                            \
+    int gkob200_implicit_residual_norm_##V(void* stream, int64_t k, const VT* tau,                 \
+                                           const VT* orig_tau, VT rel_residual_goal,               \
+                                           uint8_t stopping_id, int set_finalized,                 \
+                                           uint8_t* stop_status, uint8_t* flags);
+GKOB200_DECL_STOP(f64, double)
+GKOB200_DECL_STOP(f32, float)
+/* [ref: core/stop/criterion_kernels.hpp set_all_statuses; cuda/stop/criterion_kernels.cu:56-83] */
+int gkob200_set_all_statuses(void* stream, int64_t k, uint8_t stopping_id, int set_finalized,
+                             uint8_t* stop_status);
+
+/* ------------------------------------------------------------------------- *
+ * Scalar Jacobi  [ref: core/preconditioner/jacobi_kernels.hpp:73-107; oracle
+ * reference/preconditioner/jacobi_kernels.cpp:565-625; replaced
+ * common/unified/preconditioner/jacobi_kernels.cpp] and csr::extract_diagonal
+ * [ref: core/matrix/csr_kernels.hpp extract_diagonal; reference/matrix/csr_kernels.cpp]
+ * ------------------------------------------------------------------------- */
+#define GKOB200_DECL_JACOBI_SCALAR(V, VT)                                                          \
+    int gkob200_csr_extract_diagonal_##V##_i32(void* stream, int64_t n_rows, int64_t n_cols,       \
+                                               const int32_t* row_ptrs, const int32_t* col_idxs,   \
+                                               const VT* values, VT* diag);                        \
+    int gkob200_jacobi_invert_diagonal_##V(void* stream, int64_t n, const VT* diag, VT* inv_diag); \
+    int gkob200_jacobi_simple_scalar_apply_##V(void* stream, int64_t n, int64_t k, const VT* inv_diag, \
+                                               const VT* b, int64_t b_stride, VT* x, int64_t x_stride); \
+    int gkob200_jacobi_scalar_apply_##V(void* stream, int64_t n, int64_t k, const VT* inv_diag,    \
+                                        const VT* alpha, const VT* b, int64_t b_stride,            \
+                                        const VT* beta, VT* x, int64_t x_stride);
+GKOB200_DECL_JACOBI_SCALAR(f64, double)
+GKOB200_DECL_JACOBI_SCALAR(f32, float)
+
+/* ------------------------------------------------------------------------- *
+ * Synthetic matrix generators (HOST functions writing HOST buffers): the BASELINE
+ * shapes, rows [row_begin,row_end) of the global matrix.  kind 0: 2D 5-pt (diag 4),
+ * 1: 3D 7-pt (diag 6), 2: 3D 27-pt (diag 26); off-diagonals -1, Dirichlet truncation.
+ * [ref: the reference assembles its stencil inputs on the host the same way,
+ *  examples/distributed-solver/distributed-solver.cpp:176-186]
+ * Suffix: value type, row_ptr type, column type.
+ * ------------------------------------------------------------------------- */
+int64_t gkob200_gen_stencil_nnz(int kind, int64_t nx, int64_t ny, int64_t nz, int64_t row_begin, int64_t row_end);
+#define GKOB200_DECL_GEN(V, VT, P, PT, C, CT)                                                          \
+    int gkob200_gen_stencil_csr_##V##_##P##_##C(int kind, int64_t nx, int64_t ny, int64_t nz,          \
+                                                int64_t row_begin, int64_t row_end, PT* row_ptrs_host, \
+                                                CT* col_idxs_host, VT* values_host);
+GKOB200_DECL_GEN(f64, double, i32, int32_t, i32, int32_t)
+GKOB200_DECL_GEN(f32, float, i32, int32_t, i32, int32_t)
+GKOB200_DECL_GEN(f64, double, i64, int64_t, i64, int64_t)
+GKOB200_DECL_GEN(f32, float, i64, int64_t, i64, int64_t)
+/* power-law matrix of config 3: returns nnz */
+int64_t gkob200_gen_powerlaw_row_ptrs_i64(int64_t n, uint64_t seed, double lmin, double alpha, int64_t lmax,
+                                          int64_t* row_ptrs_host);
+int gkob200_gen_powerlaw_fill_f64_i32(int64_t n, uint64_t seed, const int64_t* row_ptrs_host,
+                                      int32_t* row_ptrs32_host, int32_t* col_idxs_host, double* values_host);
+
+#ifdef __cplusplus
+} /* extern "C" */
+#endif
+
+#include "gko_b200_solver.h"
+
+#endif /* GKO_B200_H_ */

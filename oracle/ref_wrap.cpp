@@ -1,0 +1,252 @@
+// ref_wrap.cpp — TEST INFRASTRUCTURE.  A thin C-ABI over the UNMODIFIED Ginkgo 1.5.0
+// reference / OpenMP executors built by oracle/Makefile.ref into oracle/_ref/lib.
+// It lets tests pull golden outputs from the real reference (to pin the plain-C
+// oracle and to check the CUDA path) and lets bench.py time the reference's own CPU
+// implementation (`cpu_baseline.kind == "reference"`).  Our code; it only calls
+// Ginkgo's public API.  Never loaded by the product path.
+#include <ginkgo/ginkgo.hpp>
+
+#include <omp.h>
+
+#include <chrono>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+namespace {
+
+std::shared_ptr<gko::Executor> make_exec(int kind)
+{
+    // 0: ReferenceExecutor (sequential oracle), 1: OmpExecutor (CPU baseline)
+    if (kind == 1) return gko::OmpExecutor::create();
+    return gko::ReferenceExecutor::create();
+}
+
+template <typename T>
+gko::array<T> view(std::shared_ptr<const gko::Executor> exec, int64_t n, const T* p)
+{
+    return gko::array<T>::view(exec, static_cast<gko::size_type>(n), const_cast<T*>(p));
+}
+
+template <typename V>
+std::unique_ptr<gko::matrix::Dense<V>> dense_view(std::shared_ptr<const gko::Executor> exec, int64_t n, int64_t k,
+                                                  const V* p, int64_t stride)
+{
+    return gko::matrix::Dense<V>::create(exec, gko::dim<2>(n, k), view<V>(exec, n * stride, p),
+                                         static_cast<gko::size_type>(stride));
+}
+
+template <typename V, typename I>
+std::unique_ptr<gko::matrix::Csr<V, I>> csr_view(std::shared_ptr<const gko::Executor> exec, int64_t n_rows,
+                                                 int64_t n_cols, int64_t nnz, const I* rp, const I* ci, const V* va)
+{
+    using Csr = gko::matrix::Csr<V, I>;
+    return Csr::create(exec, gko::dim<2>(n_rows, n_cols), view<V>(exec, nnz, va), view<I>(exec, nnz, ci),
+                       view<I>(exec, n_rows + 1, rp), std::make_shared<typename Csr::classical>());
+}
+
+// Records ||r|| at every iteration_complete event, the same quantity
+// stop::ResidualNorm computes from the residual (core/stop/residual_norm.cpp:196-203).
+template <typename V>
+struct HistoryLogger : gko::log::Logger {
+    mutable std::vector<double> hist;
+    mutable int64_t iters = 0;
+    void on_iteration_complete(const gko::LinOp*, const gko::size_type& it, const gko::LinOp* r, const gko::LinOp*,
+                               const gko::LinOp*) const override
+    {
+        iters = static_cast<int64_t>(it);
+        if (auto d = dynamic_cast<const gko::matrix::Dense<V>*>(r)) {
+            auto nrm = gko::matrix::Dense<V>::create(d->get_executor(), gko::dim<2>(1, d->get_size()[1]));
+            d->compute_norm2(nrm.get());
+            auto h = nrm->get_executor()->get_master();
+            hist.push_back(static_cast<double>(h->copy_val_to_host(nrm->get_const_values())));
+        }
+    }
+    HistoryLogger(std::shared_ptr<const gko::Executor> exec)
+        : gko::log::Logger(exec, gko::log::Logger::iteration_complete_mask)
+    {}
+};
+
+template <typename V, typename I>
+std::shared_ptr<gko::LinOp> to_format(std::shared_ptr<gko::matrix::Csr<V, I>> csr, int format, int64_t hybrid_limit)
+{
+    auto exec = csr->get_executor();
+    switch (format) {
+    case 0:
+        return csr;
+    case 1: {
+        auto m = gko::share(gko::matrix::Ell<V, I>::create(exec));
+        csr->convert_to(m.get());
+        return m;
+    }
+    case 2: {
+        auto m = gko::share(gko::matrix::Sellp<V, I>::create(exec));
+        csr->convert_to(m.get());
+        return m;
+    }
+    case 3: {
+        auto m = gko::share(gko::matrix::Coo<V, I>::create(exec));
+        csr->convert_to(m.get());
+        return m;
+    }
+    case 4: {
+        using Hyb = gko::matrix::Hybrid<V, I>;
+        std::shared_ptr<typename Hyb::strategy_type> strat;
+        if (hybrid_limit >= 0)
+            strat = std::make_shared<typename Hyb::column_limit>(static_cast<gko::size_type>(hybrid_limit));
+        else
+            strat = std::make_shared<typename Hyb::automatic>();
+        auto m = gko::share(Hyb::create(exec, strat));
+        csr->convert_to(m.get());
+        return m;
+    }
+    default:
+        return nullptr;
+    }
+}
+
+template <typename V, typename I>
+int spmv_impl(int exec_kind, int format, int64_t hybrid_limit, int64_t n_rows, int64_t n_cols, int64_t nnz,
+              const I* rp, const I* ci, const V* va, const V* b, int64_t bs, int64_t nrhs, const V* alpha,
+              const V* beta, V* c, int64_t cs, int reps, double* seconds)
+{
+    try {
+        auto exec = make_exec(exec_kind);
+        auto csr = gko::share(csr_view<V, I>(exec, n_rows, n_cols, nnz, rp, ci, va));
+        auto A = to_format<V, I>(csr, format, hybrid_limit);
+        if (!A) return -2;
+        auto db = dense_view<V>(exec, n_cols, nrhs, b, bs);
+        auto dc = dense_view<V>(exec, n_rows, nrhs, c, cs);
+        std::unique_ptr<gko::matrix::Dense<V>> da, dbeta;
+        if (alpha) {
+            da = gko::initialize<gko::matrix::Dense<V>>({*alpha}, exec);
+            dbeta = gko::initialize<gko::matrix::Dense<V>>({*beta}, exec);
+        }
+        double best = 1e300, total = 0;
+        for (int r = 0; r < (reps > 0 ? reps : 1); ++r) {
+            exec->synchronize();
+            auto t0 = std::chrono::steady_clock::now();
+            if (alpha)
+                A->apply(da.get(), db.get(), dbeta.get(), dc.get());
+            else
+                A->apply(db.get(), dc.get());
+            exec->synchronize();
+            const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            best = dt < best ? dt : best;
+            total += dt;
+        }
+        if (seconds) {
+            seconds[0] = total / (reps > 0 ? reps : 1);
+            seconds[1] = best;
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "ref_wrap: %s\n", e.what());
+        return -1;
+    }
+}
+
+// solver_kind 0 CG, 1 BiCGSTAB, 2 GMRES; precond_block: 0 none, 1 scalar Jacobi, >1 block Jacobi
+template <typename V, typename I>
+int64_t solve_impl(int exec_kind, int solver_kind, int format, int64_t hybrid_limit, int64_t n, int64_t nnz,
+                   const I* rp, const I* ci, const V* va, int precond_block, int64_t max_iters, double factor,
+                   int baseline, int64_t krylov_dim, int64_t nrhs, const V* b, V* x, double* hist, int64_t hist_cap,
+                   int64_t* hist_len, double* seconds)
+{
+    try {
+        auto exec = make_exec(exec_kind);
+        auto csr = gko::share(csr_view<V, I>(exec, n, n, nnz, rp, ci, va));
+        auto A = to_format<V, I>(csr, format, hybrid_limit);
+        if (!A) return -2;
+        auto db = dense_view<V>(exec, n, nrhs, b, nrhs);
+        auto dx = dense_view<V>(exec, n, nrhs, x, nrhs);
+        std::vector<std::shared_ptr<const gko::stop::CriterionFactory>> crit;
+        crit.push_back(gko::stop::Iteration::build().with_max_iters(static_cast<gko::size_type>(max_iters)).on(exec));
+        if (factor > 0) {
+            auto mode = baseline == 0   ? gko::stop::mode::rhs_norm
+                        : baseline == 1 ? gko::stop::mode::initial_resnorm
+                                        : gko::stop::mode::absolute;
+            crit.push_back(gko::stop::ResidualNorm<V>::build()
+                               .with_reduction_factor(static_cast<gko::remove_complex<V>>(factor))
+                               .with_baseline(mode)
+                               .on(exec));
+        }
+        std::shared_ptr<const gko::LinOp> M;
+        if (precond_block > 0) {
+            M = gko::preconditioner::Jacobi<V, I>::build()
+                    .with_max_block_size(static_cast<gko::uint32>(precond_block))
+                    .on(exec)
+                    ->generate(gko::as<gko::LinOp>(csr));
+        }
+        std::unique_ptr<gko::LinOp> solver;
+        if (solver_kind == 0) {
+            auto f = gko::solver::Cg<V>::build().with_criteria(crit);
+            if (M) f.with_generated_preconditioner(M);
+            solver = f.on(exec)->generate(A);
+        } else if (solver_kind == 1) {
+            auto f = gko::solver::Bicgstab<V>::build().with_criteria(crit);
+            if (M) f.with_generated_preconditioner(M);
+            solver = f.on(exec)->generate(A);
+        } else if (solver_kind == 2) {
+            auto f = gko::solver::Gmres<V>::build().with_criteria(crit).with_krylov_dim(
+                static_cast<gko::size_type>(krylov_dim));
+            if (M) f.with_generated_preconditioner(M);
+            solver = f.on(exec)->generate(A);
+        } else {
+            return -2;
+        }
+        auto logger = std::make_shared<HistoryLogger<V>>(exec);
+        solver->add_logger(logger);
+        exec->synchronize();
+        auto t0 = std::chrono::steady_clock::now();
+        solver->apply(db.get(), dx.get());
+        exec->synchronize();
+        if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        // the last iteration_complete event carries the final iteration count
+        // (core/solver/cg.cpp:163-164: logged right before the criterion check)
+        const int64_t iters = logger->iters;
+        if (hist) {
+            int64_t m = static_cast<int64_t>(logger->hist.size());
+            if (m > hist_cap) m = hist_cap;
+            for (int64_t i = 0; i < m; ++i) hist[i] = logger->hist[i];
+            if (hist_len) *hist_len = m;
+        }
+        return iters;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "ref_wrap: %s\n", e.what());
+        return -1;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int ref_num_threads(void) { return omp_get_max_threads(); }
+void ref_set_num_threads(int n) { omp_set_num_threads(n); }
+
+#define REF_SPMV(V, VT, I, IT)                                                                                   \
+    int ref_spmv_##V##_##I(int exec_kind, int format, int64_t hybrid_limit, int64_t n_rows, int64_t n_cols,      \
+                           int64_t nnz, const IT* rp, const IT* ci, const VT* va, const VT* b, int64_t bs,       \
+                           int64_t nrhs, const VT* alpha, const VT* beta, VT* c, int64_t cs, int reps,           \
+                           double* seconds)                                                                      \
+    {                                                                                                            \
+        return spmv_impl<VT, IT>(exec_kind, format, hybrid_limit, n_rows, n_cols, nnz, rp, ci, va, b, bs, nrhs,  \
+                                 alpha, beta, c, cs, reps, seconds);                                             \
+    }                                                                                                            \
+    int64_t ref_solve_##V##_##I(int exec_kind, int solver_kind, int format, int64_t hybrid_limit, int64_t n,     \
+                                int64_t nnz, const IT* rp, const IT* ci, const VT* va, int precond_block,        \
+                                int64_t max_iters, double factor, int baseline, int64_t krylov_dim,              \
+                                int64_t nrhs, const VT* b, VT* x, double* hist, int64_t hist_cap,                \
+                                int64_t* hist_len, double* seconds)                                              \
+    {                                                                                                            \
+        return solve_impl<VT, IT>(exec_kind, solver_kind, format, hybrid_limit, n, nnz, rp, ci, va,              \
+                                  precond_block, max_iters, factor, baseline, krylov_dim, nrhs, b, x, hist,      \
+                                  hist_cap, hist_len, seconds);                                                  \
+    }
+REF_SPMV(f64, double, i32, int32_t)
+REF_SPMV(f32, float, i32, int32_t)
+REF_SPMV(f64, double, i64, int64_t)
+
+}  // extern "C"

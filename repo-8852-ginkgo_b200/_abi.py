@@ -1,0 +1,109 @@
+"""ctypes declarations of the C-ABI in include/gko_b200.h / gko_b200_solver.h."""
+import ctypes as C
+
+vp, i64, i32, u8, u64, f64, f32, sz = (
+    C.c_void_p, C.c_int64, C.c_int32, C.c_uint8, C.c_uint64, C.c_double, C.c_float, C.c_size_t,
+)
+
+VT = {"f64": f64, "f32": f32}
+
+# error codes
+EINVAL, EUNSUPPORTED, EWORKSPACE = -1, -2, -3
+REDUCE_WS_BYTES = 256 + 148 * 16 * 8 * 8
+
+CSR_CLASSICAL, CSR_MERGE_PATH, CSR_AUTO = 0, 1, 2
+F64, F32 = 0, 1
+I32, I64 = 0, 1
+FMT_CSR, FMT_ELL, FMT_SELLP, FMT_COO, FMT_HYBRID = range(5)
+PRECOND_NONE, PRECOND_JACOBI_SCALAR, PRECOND_JACOBI_BLOCK = range(3)
+STOP_RHS_NORM, STOP_INITIAL_RESNORM, STOP_ABSOLUTE = range(3)
+SOLVER_CG, SOLVER_BICGSTAB, SOLVER_GMRES = range(3)
+
+
+class Matrix(C.Structure):
+    _fields_ = [
+        ("format", i32), ("value_type", i32), ("index_type", i32), ("csr_strategy", i32),
+        ("n_rows", i64), ("n_cols", i64), ("nnz", i64),
+        ("row_ptrs", vp), ("col_idxs", vp), ("values", vp),
+        ("csr_max_block_nnz", i64),
+        ("ell_stride", i64), ("ell_width", i64), ("ell_col_idxs", vp), ("ell_values", vp),
+        ("slice_size", i64), ("stride_factor", i64), ("n_slices", i64),
+        ("slice_sets", vp), ("slice_lengths", vp),
+        ("coo_nnz", i64), ("coo_row_idxs", vp), ("coo_col_idxs", vp), ("coo_values", vp),
+        ("workspace", vp), ("workspace_bytes", sz),
+    ]
+
+
+class Precond(C.Structure):
+    _fields_ = [
+        ("kind", i32), ("value_type", i32), ("inv_diag", vp),
+        ("num_blocks", i64), ("block_pointers", vp), ("blocks", vp),
+        ("block_offset", i64), ("group_offset", i64), ("group_power", i32), ("max_block_size", i32),
+    ]
+
+
+class Stop(C.Structure):
+    _fields_ = [("max_iters", i64), ("reduction_factor", f64), ("baseline", i32), ("check_every", i32)]
+
+
+def _decl(lib, name, argtypes, restype=C.c_int):
+    fn = getattr(lib, name)
+    fn.argtypes = argtypes
+    fn.restype = restype
+    return fn
+
+
+def declare(lib):
+    d = lambda name, args, res=C.c_int: _decl(lib, name, args, res)  # noqa: E731
+    d("gkob200_version", [])
+    d("gkob200_sm_count", [])
+    d("gkob200_reduce_ws_init", [vp, vp])
+    for I in ("i32", "i64"):
+        d(f"gkob200_csr_row_stats_{I}", [vp, i64, vp, vp])
+    d("gkob200_csr_pick_strategy", [i64, i64, i64, i64])
+    d("gkob200_csr_spmv_workspace_bytes", [i64, i64, i64, C.c_int], sz)
+    for V, T in VT.items():
+        for I in ("i32", "i64"):
+            d(f"gkob200_csr_spmv_{V}_{I}",
+              [vp, i64, i64, i64, vp, vp, vp, vp, i64, i64, vp, vp, vp, i64, C.c_int, i64, vp, sz])
+        d(f"gkob200_dense_fill_{V}", [vp, i64, i64, vp, i64, T])
+        d(f"gkob200_dense_copy_{V}", [vp, i64, i64, vp, i64, vp, i64])
+        d(f"gkob200_dense_scale_{V}", [vp, i64, i64, vp, i64, vp, i64])
+        d(f"gkob200_dense_inv_scale_{V}", [vp, i64, i64, vp, i64, vp, i64])
+        d(f"gkob200_dense_add_scaled_{V}", [vp, i64, i64, vp, i64, vp, i64, vp, i64])
+        d(f"gkob200_dense_sub_scaled_{V}", [vp, i64, i64, vp, i64, vp, i64, vp, i64])
+        d(f"gkob200_dense_compute_dot_{V}", [vp, i64, i64, vp, i64, vp, i64, vp, vp])
+        d(f"gkob200_dense_compute_norm2_{V}", [vp, i64, i64, vp, i64, vp, vp])
+        d(f"gkob200_dense_compute_squared_norm2_{V}", [vp, i64, i64, vp, i64, vp, vp])
+        d(f"gkob200_dense_compute_norm1_{V}", [vp, i64, i64, vp, i64, vp, vp])
+        d(f"gkob200_dense_compute_sqrt_{V}", [vp, i64, vp])
+        for I in ("i32", "i64"):
+            d(f"gkob200_dense_row_gather_{V}_{I}", [vp, i64, i64, vp, vp, i64, vp, i64])
+        d(f"gkob200_cg_initialize_{V}", [vp, i64, i64, vp, i64, vp, vp, vp, vp, i64, vp, vp, vp])
+        d(f"gkob200_cg_step_1_{V}", [vp, i64, i64, vp, vp, i64, vp, vp, vp])
+        d(f"gkob200_cg_step_2_{V}", [vp, i64, i64, vp, i64, vp, vp, vp, i64, vp, vp, vp])
+        d(f"gkob200_residual_norm_{V}", [vp, i64, vp, vp, T, u8, C.c_int, vp, vp])
+        d(f"gkob200_implicit_residual_norm_{V}", [vp, i64, vp, vp, T, u8, C.c_int, vp, vp])
+        d(f"gkob200_csr_extract_diagonal_{V}_i32", [vp, i64, i64, vp, vp, vp, vp])
+        d(f"gkob200_jacobi_invert_diagonal_{V}", [vp, i64, vp, vp])
+        d(f"gkob200_jacobi_simple_scalar_apply_{V}", [vp, i64, i64, vp, vp, i64, vp, i64])
+        d(f"gkob200_jacobi_scalar_apply_{V}", [vp, i64, i64, vp, vp, vp, i64, vp, vp, i64])
+    d("gkob200_set_all_statuses", [vp, i64, u8, C.c_int, vp])
+    # generators (host)
+    d("gkob200_gen_stencil_nnz", [C.c_int, i64, i64, i64, i64, i64], i64)
+    for V in VT:
+        for P in ("i32", "i64"):
+            d(f"gkob200_gen_stencil_csr_{V}_{P}_{P}", [C.c_int, i64, i64, i64, i64, i64, vp, vp, vp])
+    d("gkob200_gen_powerlaw_row_ptrs_i64", [i64, u64, f64, f64, i64, vp], i64)
+    d("gkob200_gen_powerlaw_fill_f64_i32", [i64, u64, vp, vp, vp, vp])
+    # operator descriptor + solver objects
+    MP, PP, SP = C.POINTER(Matrix), C.POINTER(Precond), C.POINTER(Stop)
+    d("gkob200_matrix_apply", [vp, MP, vp, i64, i64, vp, vp, vp, i64])
+    d("gkob200_solver_create", [C.c_int, MP, PP, SP, i64, i64, C.POINTER(vp)])
+    d("gkob200_solver_destroy", [vp])
+    d("gkob200_solver_apply", [vp, vp, vp, i64, vp, i64])
+    d("gkob200_solver_apply_host", [vp, vp, vp, vp])
+    d("gkob200_solver_num_iterations", [vp], i64)
+    d("gkob200_solver_stop_status", [vp, vp])
+    d("gkob200_solver_residual_history", [vp, vp, i64], i64)
+    d("gkob200_solver_launch_count", [vp], i64)

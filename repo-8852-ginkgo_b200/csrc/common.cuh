@@ -1,0 +1,160 @@
+// common.cuh — shared device/host helpers for the sm_100a sparse-solve kernels.
+//
+// Everything in csrc/ is hand-written for Blackwell B200 (sm_100a).  The
+// kernels are HBM-bound SIMT kernels (SpMV ~0.17 flop/B, BLAS-1 <= 0.125 flop/B)
+// so no tensor-core path exists here by design; the levers are coalesced /
+// vectorised streams, shared-memory (and bulk-async) staging of row blocks,
+// grids sized in multiples of the SM count and single-pass grid reductions.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gko_b200.h"
+
+namespace gkob200 {
+
+// ---- error handling --------------------------------------------------------
+// C-ABI functions never throw: they return 0 or a cudaError_t / negative code.
+#define GKOB200_CHECK_LAUNCH()                                   \
+    do {                                                         \
+        cudaError_t e__ = cudaPeekAtLastError();                 \
+        if (e__ != cudaSuccess) return static_cast<int>(e__);    \
+    } while (0)
+
+#define GKOB200_CUDA(call)                                       \
+    do {                                                         \
+        cudaError_t e__ = (call);                                \
+        if (e__ != cudaSuccess) return static_cast<int>(e__);    \
+    } while (0)
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Number of SMs of the current device (148 on B200), cached per device.
+int sm_count();
+// Largest opt-in dynamic shared memory per block of the current device.
+int max_smem_optin();
+
+inline int64_t ceildiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Grid size for a grid-stride elementwise/reduction kernel: a multiple of the
+// SM count, capped by the amount of work.
+inline int grid_for(int64_t work_items, int block, int ctas_per_sm)
+{
+    int64_t want = ceildiv(work_items, block);
+    int64_t cap = static_cast<int64_t>(sm_count()) * ctas_per_sm;
+    if (want < 1) want = 1;
+    return static_cast<int>(want < cap ? want : cap);
+}
+
+// ---- round-to-nearest, never-contracted arithmetic -------------------------
+// The parity oracle (Ginkgo's reference executor built for baseline x86-64)
+// evaluates  c += a * b  as a rounded product followed by a rounded sum.  Where
+// a kernel keeps the oracle's summation order we also keep its rounding, which
+// makes those paths bit-identical to the oracle, by using the _rn intrinsics
+// (nvcc never fuses them into FMA).
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double sqrt_rn(double a) { return __dsqrt_rn(a); }
+__device__ __forceinline__ float sqrt_rn(float a) { return __fsqrt_rn(a); }
+
+template <typename T>
+__device__ __forceinline__ T ldg(const T* p)
+{
+    return __ldg(p);
+}
+
+// gko::stopping_status is one byte: bit7 converged, bit6 finalized, bits0-5 id
+// (reference include/ginkgo/core/stop/stopping_status.hpp:104-108).
+__host__ __device__ __forceinline__ bool status_has_stopped(uint8_t s) { return (s & 0x3f) != 0; }
+__host__ __device__ __forceinline__ bool status_is_finalized(uint8_t s) { return (s & 0x40) != 0; }
+
+// ---- reductions -------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum over the block; result valid in thread 0.  `red` is >= 32 T of shared mem.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* red)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();  // protect `red` from a previous use
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    if (wid == 0) {
+        v = lane < nw ? red[lane] : T(0);
+        v = warp_sum(v);
+    }
+    return v;
+}
+
+// Single-pass deterministic grid reduction of NV running sums.
+//
+// Every block leaves its NV block-sums in `partials[blockIdx.x*NV + i]`, then
+// takes a ticket; the block that draws the last ticket re-reads all partials in
+// a fixed order (independent of which block happens to be last), reduces them
+// and hands the NV totals to `fin(totals)` on its thread 0, then re-arms the
+// ticket.  One launch, no atomics on data, run-to-run bit-reproducible for a
+// fixed grid size.  (The reference needs two launches + a tmp array:
+// common/cuda_hip/base/kernel_launch_reduction.hpp.inc:33-330.)
+template <int NV, typename T, typename Fin>
+__device__ __forceinline__ void grid_reduce(T (&v)[NV], T* partials, unsigned* ticket, Fin fin)
+{
+    __shared__ T red[32];
+    __shared__ bool is_last;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        T s = block_sum(v[i], red);
+        if (threadIdx.x == 0) partials[static_cast<size_t>(blockIdx.x) * NV + i] = s;
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    T tot[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        T s = T(0);
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x)
+            s += __ldcg(&partials[static_cast<size_t>(b) * NV + i]);
+        tot[i] = block_sum(s, red);
+    }
+    if (threadIdx.x == 0) {
+        *ticket = 0u;
+        fin(tot);
+    }
+}
+
+// Scratch carried by every reducing kernel: a ticket word followed by partials.
+// Layout of a `gkob200` reduction workspace (bytes): [0,256) ticket(s),
+// [256, ...) partial sums.  GKOB200_REDUCE_WS_BYTES is large enough for the
+// largest grid any kernel here launches (<= 148*16 blocks) times 8 values.
+constexpr int kReduceMaxBlocks = 148 * 16;
+constexpr int kReduceMaxVals = 8;
+static_assert(GKOB200_REDUCE_WS_BYTES >= 256 + kReduceMaxBlocks * kReduceMaxVals * 8, "ws");
+
+__host__ __device__ inline unsigned* ws_ticket(void* ws) { return reinterpret_cast<unsigned*>(ws); }
+template <typename T>
+__host__ __device__ inline T* ws_partials(void* ws)
+{
+    return reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + 256);
+}
+
+}  // namespace gkob200

@@ -1,0 +1,530 @@
+// csr_spmv.cu — CSR SpMV / SpMM for sm_100a.
+//
+// Replaces gko::kernels::cuda::csr::{spmv, advanced_spmv}
+// (reference cuda/matrix/csr_kernels.cu:430-542; device code
+// common/cuda_hip/matrix/csr_kernels.hpp.inc:148-483) and follows the arithmetic
+// of the oracle reference/matrix/csr_kernels.cpp:75-129.
+//
+// Two kernels, chosen once per matrix from row-length statistics:
+//
+//  * row-block ("classical"): a CTA owns 128 consecutive rows.  Their col/val
+//    streams are contiguous in memory, so the CTA copies them HBM -> shared memory
+//    with fully coalesced loads, then each thread walks ITS row out of shared
+//    memory.  Lanes of a warp are consecutive rows, so for banded / stencil
+//    matrices the gathers x[col] of a warp fall into 2-3 cache lines (the x
+//    access pattern of ELL / SELL-P, obtained on plain CSR).  Each row is summed
+//    left to right with a rounded product and a rounded add: the result is
+//    bit-identical to the reference executor.
+//
+//  * merge-path: rows+nnz are split evenly over CTAs and again over threads
+//    (Merrill & Garland), products are formed during the coalesced staging
+//    pass, each thread consumes a fixed number of merge items, partial rows are
+//    stitched with a block-wide segmented scan and per-CTA carries are applied by
+//    a small deterministic fix-up kernel (no atomics, no zero-fill pass, no
+//    allocation — the reference's merge_path allocates two arrays per call and
+//    its load_balance kernel needs a fill pass plus fp64 atomics).
+//
+// Algorithmic bytes per launch: nnz*(V+I) + (n+1)*I + n_cols*k*V + n*k*V.
+#include "internal.h"
+
+namespace gkob200 {
+namespace {
+
+constexpr int kRowsPerCta = 128;  // == blockDim.x of the row-block kernel
+
+// Shared-memory index with one padding element per 32: keeps the per-thread row
+// walks (stride = row length) conflict-free also for even row lengths.
+__device__ __forceinline__ int pad(int k) { return k + (k >> 5); }
+__host__ __device__ inline int padded_size(int cap) { return cap + (cap >> 5) + 1; }
+
+// ---------------------------------------------------------------------------
+// row-block kernel, single right-hand side
+// ---------------------------------------------------------------------------
+template <typename V, typename I, bool Advanced, bool Fused>
+__global__ void __launch_bounds__(kRowsPerCta)
+    csr_spmv_rowblock(int64_t n_rows, const I* __restrict__ row_ptrs, const I* __restrict__ col_idxs,
+                      const V* __restrict__ values, const V* __restrict__ b, int64_t b_stride,
+                      const V* __restrict__ alpha_p, const V* __restrict__ beta_p, V* __restrict__ c,
+                      int64_t c_stride, int cap, SpmvFusion<V> fu)
+{
+    if (Fused && fu.skip && *fu.skip) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    V* s_val = reinterpret_cast<V*>(smem_raw);
+    I* s_col = reinterpret_cast<I*>(s_val + padded_size(cap));
+    __shared__ I s_ptr[kRowsPerCta + 1];
+
+    const int tid = threadIdx.x;
+    const int64_t row0 = static_cast<int64_t>(blockIdx.x) * kRowsPerCta;
+    const int nrow = static_cast<int>(min(static_cast<int64_t>(kRowsPerCta), n_rows - row0));
+
+    if (tid < nrow) s_ptr[tid] = row_ptrs[row0 + tid];
+    if (tid == 0) s_ptr[nrow] = row_ptrs[row0 + nrow];
+    __syncthreads();
+    const I tile_begin = s_ptr[0];
+    const I tile_end = s_ptr[nrow];
+    const I my_begin = tid < nrow ? s_ptr[tid] : tile_end;
+    const I my_end = tid < nrow ? s_ptr[tid + 1] : tile_end;
+
+    V alpha = V(1), acc = V(0);
+    if (Advanced) {
+        alpha = *alpha_p;
+        if (tid < nrow) acc = mul_rn(c[(row0 + tid) * c_stride], *beta_p);
+    }
+
+    // The tile is processed in chunks of `cap` entries; normally (cap chosen from
+    // the matrix statistics) there is exactly one chunk.
+    for (I chunk = tile_begin; chunk < tile_end; chunk += cap) {
+        const int len = static_cast<int>(min(static_cast<I>(cap), tile_end - chunk));
+        if (chunk != tile_begin) __syncthreads();
+        // coalesced staging: consecutive threads, consecutive entries
+#pragma unroll 4
+        for (int k = tid; k < len; k += kRowsPerCta) {
+            s_col[pad(k)] = col_idxs[chunk + k];
+            s_val[pad(k)] = values[chunk + k];
+        }
+        __syncthreads();
+        // each thread walks the part of its row that lies in this chunk
+        const int lo = static_cast<int>(max(my_begin, chunk) - chunk);
+        const int hi = static_cast<int>(min(my_end, chunk + static_cast<I>(len)) - chunk);
+        for (int k = lo; k < hi; ++k) {
+            const V v = s_val[pad(k)];
+            const I col = s_col[pad(k)];
+            const V xv = ldg(b + static_cast<int64_t>(col) * b_stride);
+            acc = Advanced ? add_rn(acc, mul_rn(mul_rn(alpha, v), xv)) : add_rn(acc, mul_rn(v, xv));
+        }
+    }
+    if (tid < nrow) c[(row0 + tid) * c_stride] = acc;
+    if (Fused && fu.out) {
+        V t[1] = {tid < nrow ? acc * fu.w[row0 + tid] : V(0)};
+        V* out = fu.out;
+        grid_reduce<1>(t, ws_partials<V>(fu.ws), ws_ticket(fu.ws), [out](V(&tot)[1]) { out[0] = tot[0]; });
+    }
+}
+
+// ---------------------------------------------------------------------------
+// row-block kernel, many right-hand sides (SpMM): one warp per row, lanes over
+// the right-hand-side columns, (col,val) broadcast from shared memory; b and c
+// rows are contiguous (row-major) so every access is a full 128B/256B line.
+// ---------------------------------------------------------------------------
+template <typename V, typename I, bool Advanced>
+__global__ void __launch_bounds__(kRowsPerCta)
+    csr_spmm_rowblock(int64_t n_rows, const I* __restrict__ row_ptrs, const I* __restrict__ col_idxs,
+                      const V* __restrict__ values, const V* __restrict__ b, int64_t b_stride,
+                      int64_t nrhs, const V* __restrict__ alpha_p, const V* __restrict__ beta_p,
+                      V* __restrict__ c, int64_t c_stride, int cap)
+{
+    // 4 warps per CTA; the CTA owns 32 rows (8 per warp) so that its entry stream
+    // is long enough for coalesced staging.
+    constexpr int kRows = 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    V* s_val = reinterpret_cast<V*>(smem_raw);
+    I* s_col = reinterpret_cast<I*>(s_val + cap);
+    __shared__ I s_ptr[kRows + 1];
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int64_t row0 = static_cast<int64_t>(blockIdx.x) * kRows;
+    const int nrow = static_cast<int>(min(static_cast<int64_t>(kRows), n_rows - row0));
+    if (tid <= nrow) s_ptr[tid] = row_ptrs[row0 + tid];
+    __syncthreads();
+    const I tile_begin = s_ptr[0], tile_end = s_ptr[nrow];
+    V alpha = V(1), beta = V(0);
+    if (Advanced) {
+        alpha = *alpha_p;
+        beta = *beta_p;
+    }
+    for (int64_t j0 = 0; j0 < nrhs; j0 += 32) {
+        const int64_t j = j0 + lane;
+        const bool live = j < nrhs;
+        V acc[kRows / 4];
+#pragma unroll
+        for (int i = 0; i < kRows / 4; ++i) {
+            const int r = wid * (kRows / 4) + i;
+            acc[i] = (Advanced && live && r < nrow) ? mul_rn(c[(row0 + r) * c_stride + j], beta) : V(0);
+        }
+        for (I chunk = tile_begin; chunk < tile_end; chunk += cap) {
+            const int len = static_cast<int>(min(static_cast<I>(cap), tile_end - chunk));
+            __syncthreads();
+            for (int k = tid; k < len; k += kRowsPerCta) {
+                s_col[k] = col_idxs[chunk + k];
+                s_val[k] = values[chunk + k];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < kRows / 4; ++i) {
+                const int r = wid * (kRows / 4) + i;
+                if (r >= nrow) continue;
+                const int lo = static_cast<int>(max(s_ptr[r], chunk) - chunk);
+                const int hi = static_cast<int>(min(s_ptr[r + 1], chunk + static_cast<I>(len)) - chunk);
+                for (int k = lo; k < hi; ++k) {
+                    const V v = Advanced ? mul_rn(alpha, s_val[k]) : s_val[k];
+                    const V xv = live ? ldg(b + static_cast<int64_t>(s_col[k]) * b_stride + j) : V(0);
+                    acc[i] = add_rn(acc[i], mul_rn(v, xv));
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kRows / 4; ++i) {
+            const int r = wid * (kRows / 4) + i;
+            if (live && r < nrow) c[(row0 + r) * c_stride + j] = acc[i];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// merge-path kernel (single right-hand side)
+// ---------------------------------------------------------------------------
+constexpr int kMpThreads = 128;
+constexpr int kMpItems = 7;                            // merge items per thread (odd: conflict-free)
+constexpr int kMpTile = kMpThreads * kMpItems;         // merge items per CTA
+
+// Merge-path diagonal search: how many of the first `diag` merge items are row
+// ends.  List A = row end offsets row_ptrs[1..n], list B = 0..nnz-1; a row end is
+// consumed when row_end[r] <= current nnz index.
+template <typename I, typename P>
+__device__ __forceinline__ int64_t merge_path_search(int64_t diag, const P row_end, int64_t n_rows, int64_t nnz)
+{
+    int64_t lo = diag > nnz ? diag - nnz : 0;
+    int64_t hi = diag < n_rows ? diag : n_rows;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (static_cast<int64_t>(row_end[mid]) <= diag - mid - 1) {
+            lo = mid + 1;
+        } else {
+            hi = mid;
+        }
+    }
+    return lo;
+}
+
+template <typename V, typename I, bool Advanced>
+__global__ void __launch_bounds__(kMpThreads)
+    csr_spmv_merge(int64_t n_rows, int64_t nnz, const I* __restrict__ row_ptrs, const I* __restrict__ col_idxs,
+                   const V* __restrict__ values, const V* __restrict__ b, int64_t b_stride,
+                   const V* __restrict__ alpha_p, const V* __restrict__ beta_p, V* __restrict__ c,
+                   int64_t c_stride, int64_t* __restrict__ carry_row, V* __restrict__ carry_val)
+{
+    __shared__ V s_prod[kMpTile + 1];
+    __shared__ I s_rowend[kMpTile + 1];
+    __shared__ int64_t s_range[4];
+    __shared__ V s_scan_val[kMpThreads];
+    __shared__ int s_scan_row[kMpThreads];
+
+    const int tid = threadIdx.x;
+    const int64_t total = n_rows + nnz;
+    const int64_t diag0 = min(static_cast<int64_t>(blockIdx.x) * kMpTile, total);
+    const int64_t diag1 = min(diag0 + kMpTile, total);
+    const I* row_end = row_ptrs + 1;
+    if (tid < 2) {
+        const int64_t d = tid == 0 ? diag0 : diag1;
+        const int64_t r = merge_path_search<I>(d, row_end, n_rows, nnz);
+        s_range[tid * 2] = r;
+        s_range[tid * 2 + 1] = d - r;
+    }
+    __syncthreads();
+    const int64_t r_begin = s_range[0], k_begin = s_range[1];
+    const int64_t r_end = s_range[2], k_end = s_range[3];
+    const int n_tile_rows = static_cast<int>(r_end - r_begin);
+    const int n_tile_nnz = static_cast<int>(k_end - k_begin);
+    V alpha = V(1);
+    if (Advanced) alpha = *alpha_p;
+
+    // coalesced staging: products and row-end offsets (relative to k_begin)
+    for (int k = tid; k < n_tile_nnz; k += kMpThreads) {
+        const V v = values[k_begin + k];
+        const I col = col_idxs[k_begin + k];
+        const V xv = ldg(b + static_cast<int64_t>(col) * b_stride);
+        s_prod[k] = Advanced ? mul_rn(mul_rn(alpha, v), xv) : mul_rn(v, xv);
+    }
+    for (int r = tid; r < n_tile_rows; r += kMpThreads) {
+        s_rowend[r] = static_cast<I>(static_cast<int64_t>(row_end[r_begin + r]) - k_begin);
+    }
+    __syncthreads();
+
+    // second-level split: thread t owns merge items [t*kMpItems, (t+1)*kMpItems) of the tile
+    const int tile_items = n_tile_rows + n_tile_nnz;
+    const int d = min(tid * kMpItems, tile_items);
+    int ri, ki;
+    {
+        int lo = max(d - n_tile_nnz, 0), hi = min(d, n_tile_rows);
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (static_cast<int>(s_rowend[mid]) <= d - mid - 1) lo = mid + 1; else hi = mid;
+        }
+        ri = lo;
+        ki = d - lo;
+    }
+    V acc = V(0);
+#pragma unroll
+    for (int it = 0; it < kMpItems; ++it) {
+        if (ri + ki >= tile_items || d + it >= tile_items) break;
+        if (ri < n_tile_rows && static_cast<int>(s_rowend[ri]) <= ki) {
+            // row r_begin+ri is complete with what this thread accumulated (plus
+            // carries from earlier threads, applied below through the scan)
+            const int64_t row = r_begin + ri;
+            // mark: write partial into c now; carry-in fix-up follows
+            if (Advanced) {
+                // beta*c must be applied exactly once, by the thread that ends the row
+                c[row * c_stride] = add_rn(mul_rn(c[row * c_stride], *beta_p), acc);
+            } else {
+                c[row * c_stride] = acc;
+            }
+            acc = V(0);
+            ++ri;
+        } else {
+            acc = add_rn(acc, s_prod[ki]);
+            ++ki;
+        }
+    }
+    // carry-out of this thread: (row it was accumulating into, partial)
+    s_scan_row[tid] = ri;
+    s_scan_val[tid] = acc;
+    __syncthreads();
+    // Stitch rows that span threads: the thread that ENDS a row wrote only its own
+    // share; thread t's carry belongs to tile row s_scan_row[t].  A single pass by
+    // the threads, in order, keeps the left-to-right association: the first thread
+    // of each run of equal carry rows adds the run up and applies it.
+    {
+        const int my_row = s_scan_row[tid];
+        const bool first = (tid == 0) || (s_scan_row[tid - 1] != my_row);
+        if (first) {
+            V run = s_scan_val[tid];
+            int t = tid + 1;
+            while (t < kMpThreads && s_scan_row[t] == my_row) {
+                run = add_rn(run, s_scan_val[t]);
+                ++t;
+            }
+            if (my_row < n_tile_rows) {
+                // the row ends inside this tile (ended by thread t-1 .. or later):
+                // the ending thread stored its own share before; add the carries of
+                // the earlier threads of the run.  Only partial sums of threads
+                // strictly before the ending thread are in `run`, because the ending
+                // thread reset acc to 0 and moved on to the next row.
+                const int64_t row = r_begin + my_row;
+                c[row * c_stride] = add_rn(run, c[row * c_stride]);
+            } else {
+                // row continues into the next tile: per-CTA carry
+                carry_row[blockIdx.x] = r_begin + my_row;
+                carry_val[blockIdx.x] = run;
+            }
+        }
+    }
+    // (the last thread always ends with open row == n_tile_rows, so the leader of
+    // that run has written this tile's carry)
+}
+
+// Fix-up: tile carries belonging to the same row are consecutive; the first tile
+// of each run adds the run in order and applies it to c.  Deterministic.
+template <typename V>
+__global__ void csr_spmv_merge_fixup(int n_tiles, const int64_t* __restrict__ carry_row,
+                                     const V* __restrict__ carry_val, int64_t n_rows, V* __restrict__ c,
+                                     int64_t c_stride)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    const int64_t row = carry_row[t];
+    if (row < 0 || row >= n_rows) return;
+    if (t > 0 && carry_row[t - 1] == row) return;
+    V run = carry_val[t];
+    for (int u = t + 1; u < n_tiles && carry_row[u] == row; ++u) run = add_rn(run, carry_val[u]);
+    c[row * c_stride] = add_rn(run, c[row * c_stride]);
+}
+
+// ---------------------------------------------------------------------------
+// row statistics
+// ---------------------------------------------------------------------------
+template <typename I>
+__global__ void csr_row_stats(int64_t n_rows, const I* __restrict__ row_ptrs, unsigned long long* stats)
+{
+    unsigned long long max_row = 0, max_blk = 0, empty = 0;
+    for (int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; r < n_rows;
+         r += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const unsigned long long len = static_cast<unsigned long long>(row_ptrs[r + 1] - row_ptrs[r]);
+        max_row = max(max_row, len);
+        empty += (len == 0);
+        if (r % kRowsPerCta == 0) {
+            const int64_t e = min(r + kRowsPerCta, n_rows);
+            max_blk = max(max_blk, static_cast<unsigned long long>(row_ptrs[e] - row_ptrs[r]));
+        }
+    }
+    // integer max/sum are order independent: atomics keep this exact
+    for (int o = 16; o > 0; o >>= 1) {
+        max_row = max(max_row, __shfl_down_sync(0xffffffffu, max_row, o));
+        max_blk = max(max_blk, __shfl_down_sync(0xffffffffu, max_blk, o));
+        empty += __shfl_down_sync(0xffffffffu, empty, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(stats + 0, max_row);
+        atomicMax(stats + 1, max_blk);
+        atomicAdd(stats + 2, empty);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) stats[3] = static_cast<unsigned long long>(row_ptrs[n_rows]);
+}
+
+template <typename I>
+int row_stats_impl(void* stream, int64_t n_rows, const I* row_ptrs, int64_t* stats)
+{
+    if (n_rows < 0 || !stats) return GKOB200_EINVAL;
+    cudaStream_t s = as_stream(stream);
+    GKOB200_CUDA(cudaMemsetAsync(stats, 0, 4 * sizeof(int64_t), s));
+    if (n_rows == 0) return 0;
+    if (!row_ptrs) return GKOB200_EINVAL;
+    csr_row_stats<I><<<grid_for(n_rows, 256, 8), 256, 0, s>>>(n_rows, row_ptrs,
+                                                             reinterpret_cast<unsigned long long*>(stats));
+    GKOB200_CHECK_LAUNCH();
+    return 0;
+}
+
+inline int rowblock_cap(int64_t max_block_nnz, size_t elem_bytes)
+{
+    // shared-memory budget per CTA for the staged chunk: stays under the 48 KB
+    // static limit (>= 4 CTAs per SM); heavier blocks are processed in chunks
+    const int64_t budget = 46 * 1024 / static_cast<int64_t>(elem_bytes);
+    int64_t cap = max_block_nnz > 0 ? max_block_nnz : 2048;
+    cap = (cap + 255) / 256 * 256;
+    if (cap < 256) cap = 256;
+    if (cap > budget) cap = budget / 256 * 256;
+    return static_cast<int>(cap);
+}
+
+}  // namespace
+
+template <typename V, typename I>
+int csr_spmv_launch(cudaStream_t s, int64_t n_rows, int64_t n_cols, int64_t nnz, const I* row_ptrs,
+                    const I* col_idxs, const V* values, const V* b, int64_t b_stride, int64_t nrhs,
+                    const V* alpha, const V* beta, V* c, int64_t c_stride, int strategy,
+                    int64_t max_block_nnz, void* workspace, size_t workspace_bytes,
+                    const SpmvFusion<V>* fusion)
+{
+    if (n_rows < 0 || n_cols < 0 || nnz < 0 || nrhs < 0) return GKOB200_EINVAL;
+    if ((alpha == nullptr) != (beta == nullptr)) return GKOB200_EINVAL;
+    if (n_rows == 0 || nrhs == 0) return 0;
+    if (!row_ptrs || !c || (nnz > 0 && (!col_idxs || !values || !b))) return GKOB200_EINVAL;
+    if (b_stride < nrhs || c_stride < nrhs) return GKOB200_EINVAL;
+    const bool adv = alpha != nullptr;
+    SpmvFusion<V> fu;
+    if (fusion) fu = *fusion;
+    const bool fused = fusion != nullptr;
+
+    if (strategy == GKOB200_CSR_AUTO) {
+        strategy = max_block_nnz > 0
+                       ? gkob200_csr_pick_strategy(n_rows, nnz, -1, max_block_nnz)
+                       : GKOB200_CSR_MERGE_PATH;
+    }
+    if (nrhs > 1) {
+        if (fused) return GKOB200_EUNSUPPORTED;
+        // SpMM: warp-per-row kernel with lanes over right-hand sides
+        const int cap = 1024;
+        const size_t smem = static_cast<size_t>(cap) * (sizeof(V) + sizeof(I));
+        const int64_t grid = ceildiv(n_rows, 32);
+        if (adv)
+            csr_spmm_rowblock<V, I, true><<<static_cast<unsigned>(grid), kRowsPerCta, smem, s>>>(
+                n_rows, row_ptrs, col_idxs, values, b, b_stride, nrhs, alpha, beta, c, c_stride, cap);
+        else
+            csr_spmm_rowblock<V, I, false><<<static_cast<unsigned>(grid), kRowsPerCta, smem, s>>>(
+                n_rows, row_ptrs, col_idxs, values, b, b_stride, nrhs, alpha, beta, c, c_stride, cap);
+        GKOB200_CHECK_LAUNCH();
+        return 0;
+    }
+    if (strategy == GKOB200_CSR_CLASSICAL) {
+        const int cap = rowblock_cap(max_block_nnz, sizeof(V) + sizeof(I));
+        const size_t smem = static_cast<size_t>(padded_size(cap)) * (sizeof(V) + sizeof(I)) + 16;
+        const unsigned grid = static_cast<unsigned>(ceildiv(n_rows, kRowsPerCta));
+        if (fused && grid > static_cast<unsigned>(kReduceMaxBlocks) * kReduceMaxVals) return GKOB200_EUNSUPPORTED;
+#define GKOB200_RB(ADV, FUSED)                                                                        \
+    csr_spmv_rowblock<V, I, ADV, FUSED><<<grid, kRowsPerCta, smem, s>>>(                              \
+        n_rows, row_ptrs, col_idxs, values, b, b_stride, alpha, beta, c, c_stride, cap, fu)
+        if (adv && fused) GKOB200_RB(true, true);
+        else if (adv) GKOB200_RB(true, false);
+        else if (fused) GKOB200_RB(false, true);
+        else GKOB200_RB(false, false);
+#undef GKOB200_RB
+        GKOB200_CHECK_LAUNCH();
+        return 0;
+    }
+    if (strategy != GKOB200_CSR_MERGE_PATH) return GKOB200_EINVAL;
+    if (fused && (fu.out || fu.skip)) return GKOB200_EUNSUPPORTED;
+    const int64_t n_tiles = ceildiv(n_rows + nnz, kMpTile);
+    const size_t need = gkob200_csr_spmv_workspace_bytes(n_rows, nnz, nrhs, sizeof(V));
+    if (!workspace || workspace_bytes < need) return GKOB200_EWORKSPACE;
+    int64_t* carry_row = reinterpret_cast<int64_t*>(workspace);
+    V* carry_val = reinterpret_cast<V*>(carry_row + n_tiles);
+    if (adv)
+        csr_spmv_merge<V, I, true><<<static_cast<unsigned>(n_tiles), kMpThreads, 0, s>>>(
+            n_rows, nnz, row_ptrs, col_idxs, values, b, b_stride, alpha, beta, c, c_stride, carry_row,
+            carry_val);
+    else
+        csr_spmv_merge<V, I, false><<<static_cast<unsigned>(n_tiles), kMpThreads, 0, s>>>(
+            n_rows, nnz, row_ptrs, col_idxs, values, b, b_stride, alpha, beta, c, c_stride, carry_row,
+            carry_val);
+    GKOB200_CHECK_LAUNCH();
+    csr_spmv_merge_fixup<V><<<static_cast<unsigned>(ceildiv(n_tiles, 256)), 256, 0, s>>>(
+        static_cast<int>(n_tiles), carry_row, carry_val, n_rows, c, c_stride);
+    GKOB200_CHECK_LAUNCH();
+    return 0;
+}
+
+#define GKOB200_INST(V, I)                                                                              \
+    template int csr_spmv_launch<V, I>(cudaStream_t, int64_t, int64_t, int64_t, const I*, const I*,     \
+                                       const V*, const V*, int64_t, int64_t, const V*, const V*, V*,    \
+                                       int64_t, int, int64_t, void*, size_t, const SpmvFusion<V>*);
+GKOB200_INST(double, int32_t)
+GKOB200_INST(float, int32_t)
+GKOB200_INST(double, int64_t)
+GKOB200_INST(float, int64_t)
+#undef GKOB200_INST
+
+}  // namespace gkob200
+
+using namespace gkob200;
+
+extern "C" {
+
+size_t gkob200_csr_spmv_workspace_bytes(int64_t n_rows, int64_t nnz, int64_t nrhs, int value_bytes)
+{
+    (void)nrhs;
+    const int64_t n_tiles = ceildiv(n_rows + nnz, kMpTile) + 1;
+    return static_cast<size_t>(n_tiles) * (sizeof(int64_t) + static_cast<size_t>(value_bytes)) + 64;
+}
+
+int gkob200_csr_pick_strategy(int64_t n_rows, int64_t nnz, int64_t max_row_nnz, int64_t max_block_nnz)
+{
+    // The row-block kernel is the right choice while a block of 128 rows is close
+    // to the average block (regular matrices: stencils, FEM, banded).  A block much
+    // heavier than average means skewed rows: thread-per-row would serialise on the
+    // long rows, so the nnz-balanced merge-path kernel takes over.
+    if (n_rows <= 0 || nnz <= 0) return GKOB200_CSR_CLASSICAL;
+    const double mean_block = static_cast<double>(nnz) / static_cast<double>(ceildiv(n_rows, kRowsPerCta));
+    const double mean_row = static_cast<double>(nnz) / static_cast<double>(n_rows);
+    if (max_block_nnz > 0 && static_cast<double>(max_block_nnz) > 4.0 * mean_block + 1024.0)
+        return GKOB200_CSR_MERGE_PATH;
+    if (max_row_nnz > 0 && static_cast<double>(max_row_nnz) > 8.0 * mean_row + 256.0)
+        return GKOB200_CSR_MERGE_PATH;
+    return GKOB200_CSR_CLASSICAL;
+}
+
+int gkob200_csr_row_stats_i32(void* stream, int64_t n_rows, const int32_t* row_ptrs, int64_t* stats)
+{
+    return row_stats_impl<int32_t>(stream, n_rows, row_ptrs, stats);
+}
+int gkob200_csr_row_stats_i64(void* stream, int64_t n_rows, const int64_t* row_ptrs, int64_t* stats)
+{
+    return row_stats_impl<int64_t>(stream, n_rows, row_ptrs, stats);
+}
+
+#define GKOB200_DEF_CSR_SPMV(V, VT, I, IT)                                                            \
+    int gkob200_csr_spmv_##V##_##I(void* stream, int64_t n_rows, int64_t n_cols, int64_t nnz,         \
+                                   const IT* row_ptrs, const IT* col_idxs, const VT* values,          \
+                                   const VT* b, int64_t b_stride, int64_t nrhs, const VT* alpha,      \
+                                   const VT* beta, VT* c, int64_t c_stride, int strategy,             \
+                                   int64_t max_block_nnz, void* workspace, size_t workspace_bytes)    \
+    {                                                                                                 \
+        return csr_spmv_launch<VT, IT>(as_stream(stream), n_rows, n_cols, nnz, row_ptrs, col_idxs,    \
+                                       values, b, b_stride, nrhs, alpha, beta, c, c_stride, strategy, \
+                                       max_block_nnz, workspace, workspace_bytes, nullptr);           \
+    }
+GKOB200_DEF_CSR_SPMV(f64, double, i32, int32_t)
+GKOB200_DEF_CSR_SPMV(f32, float, i32, int32_t)
+GKOB200_DEF_CSR_SPMV(f64, double, i64, int64_t)
+GKOB200_DEF_CSR_SPMV(f32, float, i64, int64_t)
+
+}  // extern "C"

@@ -1,0 +1,36 @@
+// internal.h — C++ entry points shared between translation units of libgko_b200.so
+// (not part of the C-ABI).
+#pragma once
+#include "common.cuh"
+
+namespace gkob200 {
+
+// Optional fusions for an SpMV launch issued from inside a solver iteration:
+//  skip : device flag; a non-zero value turns the launch into a no-op (the solver
+//         has stopped — mirrors the reference's per-column has_stopped() guards)
+//  w/out: additionally compute out[0] = sum_i w[i] * (A b)[i] in the same pass
+//         (single-pass grid reduction through `ws`)
+template <typename V>
+struct SpmvFusion {
+    const int* skip = nullptr;
+    const V* w = nullptr;
+    V* out = nullptr;
+    void* ws = nullptr;
+};
+
+template <typename V, typename I>
+int csr_spmv_launch(cudaStream_t s, int64_t n_rows, int64_t n_cols, int64_t nnz, const I* row_ptrs,
+                    const I* col_idxs, const V* values, const V* b, int64_t b_stride, int64_t nrhs,
+                    const V* alpha, const V* beta, V* c, int64_t c_stride, int strategy,
+                    int64_t max_block_nnz, void* workspace, size_t workspace_bytes,
+                    const SpmvFusion<V>* fusion);
+
+// y = A x (alpha == beta == nullptr) or y = alpha A x + beta y, any format.
+template <typename V>
+int matrix_apply(cudaStream_t s, const gkob200_matrix& A, const V* b, int64_t b_stride, int64_t nrhs,
+                 const V* alpha, const V* beta, V* c, int64_t c_stride, const SpmvFusion<V>* fusion);
+
+// true if matrix_apply honours fusion->w/out itself for this descriptor
+bool matrix_apply_fuses_dot(const gkob200_matrix& A, int64_t nrhs);
+
+}  // namespace gkob200
