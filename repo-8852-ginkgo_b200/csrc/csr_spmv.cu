@@ -25,6 +25,8 @@
 //    its load_balance kernel needs a fill pass plus fp64 atomics).
 //
 // Algorithmic bytes per launch: nnz*(V+I) + (n+1)*I + n_cols*k*V + n*k*V.
+#include <cstdlib>
+
 #include "internal.h"
 
 namespace gkob200 {
@@ -36,6 +38,42 @@ constexpr int kRowsPerCta = 128;  // == blockDim.x of the row-block kernel
 // walks (stride = row length) conflict-free also for even row lengths.
 __device__ __forceinline__ int pad(int k) { return k + (k >> 5); }
 __host__ __device__ inline int padded_size(int cap) { return cap + (cap >> 5) + 1; }
+__host__ __device__ inline size_t align16(size_t b) { return (b + 15) & ~static_cast<size_t>(15); }
+
+// ---- bulk asynchronous copy (TMA engine, 1-D) + mbarrier, raw PTX ------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completion
+// is signalled on `bar` as transaction bytes.  SASS: UBLKCP.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 
 // ---------------------------------------------------------------------------
 // row-block kernel, single right-hand side
@@ -50,7 +88,7 @@ __global__ void __launch_bounds__(kRowsPerCta)
     if (Fused && fu.skip && *fu.skip) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     V* s_val = reinterpret_cast<V*>(smem_raw);
-    I* s_col = reinterpret_cast<I*>(s_val + padded_size(cap));
+    I* s_col = reinterpret_cast<I*>(smem_raw + align16(static_cast<size_t>(padded_size(cap)) * sizeof(V)));
     __shared__ I s_ptr[kRowsPerCta + 1];
 
     const int tid = threadIdx.x;
@@ -91,6 +129,106 @@ __global__ void __launch_bounds__(kRowsPerCta)
             const I col = s_col[pad(k)];
             const V xv = ldg(b + static_cast<int64_t>(col) * b_stride);
             acc = Advanced ? add_rn(acc, mul_rn(mul_rn(alpha, v), xv)) : add_rn(acc, mul_rn(v, xv));
+        }
+    }
+    if (tid < nrow) c[(row0 + tid) * c_stride] = acc;
+    if (Fused && fu.out) {
+        V t[1] = {tid < nrow ? acc * fu.w[row0 + tid] : V(0)};
+        V* out = fu.out;
+        grid_reduce<1>(t, ws_partials<V>(fu.ws), ws_ticket(fu.ws), [out](V(&tot)[1]) { out[0] = tot[0]; });
+    }
+}
+
+// ---------------------------------------------------------------------------
+// row-block kernel, bulk-async staging: the CTA's col/val streams are two
+// contiguous byte ranges, so ONE thread hands them to the TMA engine
+// (cp.async.bulk) and the whole tile is in flight at once — no register staging,
+// no per-thread load loop; the other threads meanwhile fetch the row pointers and
+// the (at most 3) tail elements the 16-byte granularity leaves over.
+// Requires 16-byte aligned `values` / `col_idxs` base pointers.
+// ---------------------------------------------------------------------------
+template <typename V, typename I, bool Advanced, bool Fused>
+__global__ void __launch_bounds__(kRowsPerCta)
+    csr_spmv_rowblock_tma(int64_t n_rows, const I* __restrict__ row_ptrs, const I* __restrict__ col_idxs,
+                          const V* __restrict__ values, const V* __restrict__ b, int64_t b_stride,
+                          const V* __restrict__ alpha_p, const V* __restrict__ beta_p, V* __restrict__ c,
+                          int64_t c_stride, int cap, SpmvFusion<V> fu)
+{
+    if (Fused && fu.skip && *fu.skip) return;
+    constexpr int VA = 16 / sizeof(V);  // elements per 16 bytes
+    constexpr int IA = 16 / sizeof(I);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    V* s_val = reinterpret_cast<V*>(smem_raw);
+    I* s_col = reinterpret_cast<I*>(smem_raw + align16(static_cast<size_t>(cap + VA) * sizeof(V)));
+    __shared__ I s_ptr[kRowsPerCta + 1];
+    __shared__ __align__(8) uint64_t bar;
+
+    const int tid = threadIdx.x;
+    const int64_t row0 = static_cast<int64_t>(blockIdx.x) * kRowsPerCta;
+    const int nrow = static_cast<int>(min(static_cast<int64_t>(kRowsPerCta), n_rows - row0));
+    if (tid == 0) mbar_init(&bar, 1);
+    // every thread reads its own two row pointers (coalesced, overlapping by one)
+    const I my_begin = row_ptrs[row0 + min(tid, nrow)];
+    const I my_end = row_ptrs[row0 + min(tid + 1, nrow)];
+    if (tid == 0) s_ptr[0] = my_begin;
+    if (tid == nrow - 1) s_ptr[1] = my_end;
+    __syncthreads();
+    const I tile_begin = s_ptr[0];
+    const I tile_end = s_ptr[1];
+
+    V alpha = V(1), acc = V(0);
+    if (Advanced) {
+        alpha = *alpha_p;
+        if (tid < nrow) acc = mul_rn(c[(row0 + tid) * c_stride], *beta_p);
+    }
+    unsigned parity = 0;
+    for (I chunk = tile_begin; chunk < tile_end; chunk += cap) {
+        const I chunk_end = min(chunk + static_cast<I>(cap), tile_end);
+        // 16-byte aligned windows [vb, vf) / [cb, cf) go through the bulk copy; smem
+        // index of global entry g is g - vb (values) / g - cb (columns)
+        const I vb = chunk & ~static_cast<I>(VA - 1), vf = chunk_end & ~static_cast<I>(VA - 1);
+        const I cb = chunk & ~static_cast<I>(IA - 1), cf = chunk_end & ~static_cast<I>(IA - 1);
+        if (chunk != tile_begin) __syncthreads();  // everyone is done with the previous chunk
+        if (tid == 0) {
+            const unsigned vbytes = vf > vb ? static_cast<unsigned>((vf - vb) * sizeof(V)) : 0u;
+            const unsigned cbytes = cf > cb ? static_cast<unsigned>((cf - cb) * sizeof(I)) : 0u;
+            mbar_expect_tx(&bar, vbytes + cbytes);
+            if (vbytes) bulk_g2s(s_val, values + vb, vbytes, &bar);
+            if (cbytes) bulk_g2s(s_col, col_idxs + cb, cbytes, &bar);
+        }
+        // tails (< 16 bytes each) with plain loads
+        {
+            const I vt = vf > vb ? vf : vb;
+            if (tid < VA && vt + tid < chunk_end) s_val[vt + tid - vb] = values[vt + tid];
+            const I ct = cf > cb ? cf : cb;
+            if (tid >= 32 && tid < 32 + IA && ct + (tid - 32) < chunk_end)
+                s_col[ct + (tid - 32) - cb] = col_idxs[ct + (tid - 32)];
+        }
+        mbar_wait(&bar, parity);
+        parity ^= 1u;
+        __syncthreads();  // tails visible
+        const I lo = max(my_begin, chunk), hi = min(my_end, chunk_end);
+        const V* sv = s_val - vb;  // index with the global entry number
+        const I* sc = s_col - cb;
+        // batches of kBatch entries: all gathers of a batch are issued before the first
+        // add, so a thread keeps kBatch L2/L1 requests in flight; the adds stay in
+        // storage order (bit-identical to the oracle)
+        constexpr int kBatch = 9;
+        for (I k = lo; k < hi; k += kBatch) {
+            V v[kBatch], xv[kBatch];
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const bool in = k + u < hi;
+                v[u] = in ? sv[k + u] : V(0);
+                const I col = in ? sc[k + u] : I(0);
+                xv[u] = in ? ldg(b + static_cast<int64_t>(col) * b_stride) : V(0);
+            }
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                if (k + u < hi)
+                    acc = Advanced ? add_rn(acc, mul_rn(mul_rn(alpha, v[u]), xv[u]))
+                                   : add_rn(acc, mul_rn(v[u], xv[u]));
+            }
         }
     }
     if (tid < nrow) c[(row0 + tid) * c_stride] = acc;
@@ -374,6 +512,18 @@ int row_stats_impl(void* stream, int64_t n_rows, const I* row_ptrs, int64_t* sta
     return 0;
 }
 
+// 1: bulk-async (TMA) staging [default], 0: register-staged loads.  The environment
+// variable only exists to A/B the two on the GPU box (profiles/).
+inline int rowblock_variant()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GKOB200_CSR_ROWBLOCK");
+        v = (e && e[0] == 'p') ? 0 : 1;
+    }
+    return v;
+}
+
 inline int rowblock_cap(int64_t max_block_nnz, size_t elem_bytes)
 {
     // shared-memory budget per CTA for the staged chunk: stays under the 48 KB
@@ -427,9 +577,24 @@ int csr_spmv_launch(cudaStream_t s, int64_t n_rows, int64_t n_cols, int64_t nnz,
     }
     if (strategy == GKOB200_CSR_CLASSICAL) {
         const int cap = rowblock_cap(max_block_nnz, sizeof(V) + sizeof(I));
-        const size_t smem = static_cast<size_t>(padded_size(cap)) * (sizeof(V) + sizeof(I)) + 16;
+        const size_t smem = align16(static_cast<size_t>(padded_size(cap)) * sizeof(V)) +
+                            align16(static_cast<size_t>(padded_size(cap)) * sizeof(I)) + 64;
         const unsigned grid = static_cast<unsigned>(ceildiv(n_rows, kRowsPerCta));
-        if (fused && grid > static_cast<unsigned>(kReduceMaxBlocks) * kReduceMaxVals) return GKOB200_EUNSUPPORTED;
+        const bool aligned = (reinterpret_cast<uintptr_t>(values) % 16 == 0) &&
+                             (reinterpret_cast<uintptr_t>(col_idxs) % 16 == 0);
+        if (aligned && rowblock_variant() == 1) {
+#define GKOB200_RBT(ADV, FUSED)                                                                       \
+    csr_spmv_rowblock_tma<V, I, ADV, FUSED><<<grid, kRowsPerCta, smem, s>>>(                          \
+        n_rows, row_ptrs, col_idxs, values, b, b_stride, alpha, beta, c, c_stride, cap, fu)
+            if (adv && fused) GKOB200_RBT(true, true);
+            else if (adv) GKOB200_RBT(true, false);
+            else if (fused) GKOB200_RBT(false, true);
+            else GKOB200_RBT(false, false);
+#undef GKOB200_RBT
+            GKOB200_CHECK_LAUNCH();
+            return 0;
+        }
+        if (fused && fu.out && static_cast<int64_t>(grid) > fu.ws_blocks) return GKOB200_EWORKSPACE;
 #define GKOB200_RB(ADV, FUSED)                                                                        \
     csr_spmv_rowblock<V, I, ADV, FUSED><<<grid, kRowsPerCta, smem, s>>>(                              \
         n_rows, row_ptrs, col_idxs, values, b, b_stride, alpha, beta, c, c_stride, cap, fu)

@@ -16,6 +16,7 @@ struct SpmvFusion {
     const V* w = nullptr;
     V* out = nullptr;
     void* ws = nullptr;
+    int64_t ws_blocks = 0;  // number of per-block partials `ws` has room for
 };
 
 template <typename V, typename I>

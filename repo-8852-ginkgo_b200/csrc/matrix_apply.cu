@@ -13,8 +13,7 @@ bool matrix_apply_fuses_dot(const gkob200_matrix& A, int64_t nrhs)
             strategy = A.csr_max_block_nnz > 0
                            ? gkob200_csr_pick_strategy(A.n_rows, A.nnz, -1, A.csr_max_block_nnz)
                            : GKOB200_CSR_MERGE_PATH;
-        return strategy == GKOB200_CSR_CLASSICAL &&
-               ceildiv(A.n_rows, 128) <= static_cast<int64_t>(kReduceMaxBlocks) * kReduceMaxVals;
+        return strategy == GKOB200_CSR_CLASSICAL;
     }
     return false;
 }

@@ -165,15 +165,18 @@ struct CgSolver : gkob200_solver {
     SolverState* h_state = nullptr;  // pinned, 2 slots
     cudaEvent_t ev[2] = {nullptr, nullptr};
     cudaGraphExec_t graph = nullptr;
+    cudaStream_t cap_stream = nullptr;  // capture stream (the legacy default stream cannot be captured)
     void* graph_x = nullptr;
     int64_t graph_xs = 0;
     int chunk = 8;
     int64_t launches_per_iter = 0;
+    int64_t ws_blocks = 0;
     DevBuf host_b, host_x;  // device staging for apply_host
 
     ~CgSolver()
     {
         if (graph) cudaGraphExecDestroy(graph);
+        if (cap_stream) cudaStreamDestroy(cap_stream);
         if (h_state) cudaFreeHost(h_state);
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);
@@ -191,9 +194,14 @@ struct CgSolver : gkob200_solver {
         if ((rc = status.alloc(static_cast<size_t>(k) + 16))) return rc;
         const int64_t hist_len = stop.max_iters + 2 < (int64_t(1) << 24) ? stop.max_iters + 2 : (int64_t(1) << 24);
         if ((rc = hist.alloc(static_cast<size_t>(hist_len) * sizeof(V)))) return rc;
-        if ((rc = ws.alloc(GKOB200_REDUCE_WS_BYTES))) return rc;
+        // reduction scratch: room for one partial per CTA of the largest grid any fused
+        // kernel launches (the SpMV with the fused dot runs one CTA per 128 rows)
+        ws_blocks = ceildiv(n, 128) + 1;
+        if (ws_blocks < kReduceMaxBlocks) ws_blocks = kReduceMaxBlocks;
+        if ((rc = ws.alloc(256 + static_cast<size_t>(ws_blocks) * kReduceMaxVals * sizeof(double)))) return rc;
         GKOB200_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h_state), 2 * sizeof(SolverState), cudaHostAllocDefault));
         for (auto& e : ev) GKOB200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        GKOB200_CUDA(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
         stop_status_host.assign(k, 0);
         return 0;
     }
@@ -268,6 +276,7 @@ struct CgSolver : gkob200_solver {
             fu.w = p();
             fu.out = sc(S_BETA);
             fu.ws = ws.p;
+            fu.ws_blocks = ws_blocks;
         }
         int rc = matrix_apply<V>(s, A, p(), 1, 1, nullptr, nullptr, q(), 1, &fu);
         if (rc) return rc;
@@ -280,8 +289,9 @@ struct CgSolver : gkob200_solver {
         return enqueue_update<false>(s, x);
     }
 
-    int build_graph(cudaStream_t s, V* x, int64_t xs)
+    int build_graph(V* x, int64_t xs)
     {
+        cudaStream_t s = cap_stream;
         if (graph && graph_x == x && graph_xs == xs) return 0;
         if (graph) {
             cudaGraphExecDestroy(graph);
@@ -331,10 +341,17 @@ struct CgSolver : gkob200_solver {
         if ((rc = enqueue_update<true>(s, x))) return rc;
         // ---- iterations: graph of `chunk` iterations, host polls the stop flag one
         //      chunk behind so the device never idles ------------------------------
-        if ((rc = build_graph(s, x, xs))) return rc;
+        if ((rc = build_graph(x, xs))) return rc;
         int64_t g = 0;
         bool done = false;
+        // after ceil(max_iters / chunk) chunks the Iteration criterion has fired for
+        // certain: never enqueue beyond that, just wait for the flag
+        const int64_t max_chunks = ceildiv(stop.max_iters, chunk);
         while (!done) {
+            if (g >= max_chunks) {
+                GKOB200_CUDA(cudaStreamSynchronize(s));
+                break;
+            }
             GKOB200_CUDA(cudaGraphLaunch(graph, s));
             launch_count += launches_per_iter * chunk;
             const int slot = static_cast<int>(g & 1);

@@ -1,0 +1,31 @@
+#!/usr/bin/env python
+"""Summarise an .ncu-rep (read here, no GPU): python tools/ncu_summary.py file.ncu-rep [more metrics]"""
+import csv
+import subprocess
+import sys
+
+KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'dram__cycles_active.avg.pct_of_peak_sustained_elapsed',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread',
+        'launch__occupancy_limit_shared_mem', 'launch__occupancy_limit_registers', 'launch__occupancy_limit_warps',
+        'launch__grid_size', 'launch__block_size', 'launch__shared_mem_per_block_dynamic',
+        'launch__shared_mem_per_block_static',
+        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct',
+        'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__throughput.avg.pct_of_peak_sustained_elapsed',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'lts__t_bytes.sum', 'l1tex__t_bytes.sum',
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'smsp__inst_executed.sum',
+        'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum',
+        'smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio' ]
+out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+hdr, units = rows[0], rows[1]
+extra = sys.argv[2:]
+for r in rows[2:]:
+    print("==", r[hdr.index("Kernel Name")][:150])
+    for k in KEYS + extra:
+        if k in hdr:
+            print(f"  {k} = {r[hdr.index(k)]} {units[hdr.index(k)]}")
+    st = [(float(r[i].replace(',', '')), h) for i, h in enumerate(hdr)
+          if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("per_issue_active.ratio") and r[i]]
+    for v, h in sorted(st, reverse=True)[:8]:
+        print(f"  stall {h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', '')} = {v:.2f}")
