@@ -95,6 +95,87 @@ GKOB200_DECL_CSR_SPMV(f32, float, i64, int64_t)
 size_t gkob200_csr_spmv_workspace_bytes(int64_t n_rows, int64_t nnz, int64_t nrhs, int value_bytes);
 
 /* ------------------------------------------------------------------------- *
+ * ELL / SELL-P / COO SpMV and SpMM
+ * [ref: core/matrix/ell_kernels.hpp:52-66, sellp_kernels.hpp:52-63, coo_kernels.hpp:53-76;
+ *  oracle reference/matrix/{ell,sellp,coo}_kernels.cpp; replaced
+ *  cuda/matrix/{ell,sellp,coo}_kernels.cu]
+ * ELL: col_idxs/values[stride*width], entry (row,i) at row + i*stride, padding col -1.
+ * SELL-P: entry (row,i) of slice s at (slice_sets[s]+i)*slice_size + row%slice_size;
+ *         slice_sets / slice_lengths are size_type (uint64) like the reference's.
+ * COO: row-sorted triplets; coo_spmv2 ACCUMULATES (c += [alpha] A b), the building block
+ *      of Hybrid::apply [ref: core/matrix/hybrid.cpp:133-160].  workspace: carries.
+ * alpha/beta: both NULL (simple apply) or both set (coo_spmv2: alpha alone, nullable).
+ * ------------------------------------------------------------------------- */
+size_t gkob200_coo_spmv_workspace_bytes(int64_t nnz, int value_bytes);
+#define GKOB200_DECL_FMT(V, VT, I, IT)                                                                         \
+    int gkob200_ell_spmv_##V##_##I(void* stream, int64_t n_rows, int64_t n_cols, int64_t stride, int64_t width, \
+                                   const IT* col_idxs, const VT* values, const VT* b, int64_t b_stride,         \
+                                   int64_t nrhs, const VT* alpha, const VT* beta, VT* c, int64_t c_stride);     \
+    int gkob200_sellp_spmv_##V##_##I(void* stream, int64_t n_rows, int64_t n_cols, int64_t slice_size,          \
+                                     const uint64_t* slice_sets, const uint64_t* slice_lengths,                 \
+                                     const IT* col_idxs, const VT* values, const VT* b, int64_t b_stride,       \
+                                     int64_t nrhs, const VT* alpha, const VT* beta, VT* c, int64_t c_stride);   \
+    int gkob200_coo_spmv_##V##_##I(void* stream, int64_t n_rows, int64_t n_cols, int64_t nnz,                   \
+                                   const IT* row_idxs, const IT* col_idxs, const VT* values, const VT* b,       \
+                                   int64_t b_stride, int64_t nrhs, const VT* alpha, const VT* beta, VT* c,      \
+                                   int64_t c_stride, void* workspace, size_t workspace_bytes);                  \
+    int gkob200_coo_spmv2_##V##_##I(void* stream, int64_t n_rows, int64_t n_cols, int64_t nnz,                  \
+                                    const IT* row_idxs, const IT* col_idxs, const VT* values, const VT* b,      \
+                                    int64_t b_stride, int64_t nrhs, const VT* alpha, VT* c, int64_t c_stride,   \
+                                    void* workspace, size_t workspace_bytes);
+GKOB200_DECL_FMT(f64, double, i32, int32_t)
+GKOB200_DECL_FMT(f32, float, i32, int32_t)
+GKOB200_DECL_FMT(f64, double, i64, int64_t)
+GKOB200_DECL_FMT(f32, float, i64, int64_t)
+
+/* ------------------------------------------------------------------------- *
+ * Integer / index kernels (bit-exact with the reference executor)
+ * [ref: core/components/prefix_sum_kernels.hpp:67 (exclusive scan, last entry receives the
+ *  total), common/unified/components/format_conversion_kernels.cpp:49-112,
+ *  reference/matrix/sellp_kernels.cpp:134-160 compute_slice_sets,
+ *  reference/matrix/ell_kernels.cpp:159-168 compute_max_row_nnz,
+ *  common/unified/matrix/hybrid_kernels.cpp:51-76 compute_coo_row_ptrs,
+ *  common/unified/matrix/csr_kernels.cpp:137-243 convert_to_{sellp,ell,hybrid}]
+ * ws: gkob200_prefix_sum_workspace_bytes(n) bytes of scratch.
+ * ------------------------------------------------------------------------- */
+size_t gkob200_prefix_sum_workspace_bytes(int64_t n);
+int gkob200_prefix_sum_i32(void* stream, int32_t* data, int64_t n, void* ws, size_t ws_bytes);
+int gkob200_prefix_sum_i64(void* stream, int64_t* data, int64_t n, void* ws, size_t ws_bytes);
+int gkob200_prefix_sum_u64(void* stream, uint64_t* data, int64_t n, void* ws, size_t ws_bytes);
+int gkob200_hybrid_compute_coo_row_ptrs(void* stream, const uint64_t* row_nnz, int64_t n, uint64_t ell_lim,
+                                        int64_t* coo_row_ptrs, void* ws, size_t ws_bytes);
+#define GKOB200_DECL_CONV_I(I, IT)                                                                             \
+    int gkob200_convert_ptrs_to_idxs_##I(void* stream, const IT* ptrs, int64_t n, IT* idxs);                    \
+    int gkob200_convert_idxs_to_ptrs_##I(void* stream, const IT* idxs, int64_t num_idxs, int64_t n, IT* ptrs);  \
+    int gkob200_convert_ptrs_to_sizes_##I(void* stream, const IT* ptrs, int64_t n, uint64_t* sizes);            \
+    int gkob200_compute_max_row_nnz_##I(void* stream, const IT* row_ptrs, int64_t n, uint64_t* max_nnz);        \
+    int gkob200_sellp_compute_slice_sets_##I(void* stream, const IT* row_ptrs, int64_t n, int64_t slice_size,   \
+                                             int64_t stride_factor, uint64_t* slice_sets,                      \
+                                             uint64_t* slice_lengths, void* ws, size_t ws_bytes);              \
+    /* hist[b] = #rows with lo + b*width <= row length < lo + (b+1)*width, b < bins <= 8192; used to take   \
+     * the order statistics Hybrid's imbalance_limit strategies need without sorting on the host */          \
+    int gkob200_row_len_histogram_##I(void* stream, const IT* row_ptrs, int64_t n, uint64_t lo, uint64_t width, \
+                                      int bins, uint64_t* hist);
+GKOB200_DECL_CONV_I(i32, int32_t)
+GKOB200_DECL_CONV_I(i64, int64_t)
+#define GKOB200_DECL_CONV_VI(V, VT, I, IT)                                                                     \
+    int gkob200_csr_convert_to_ell_##V##_##I(void* stream, int64_t n, const IT* row_ptrs, const IT* col_idxs,   \
+                                             const VT* values, int64_t ell_width, int64_t ell_stride,          \
+                                             IT* ell_col_idxs, VT* ell_values);                                \
+    int gkob200_csr_convert_to_sellp_##V##_##I(void* stream, int64_t n, const IT* row_ptrs,                     \
+                                               const IT* col_idxs, const VT* values, int64_t slice_size,       \
+                                               const uint64_t* slice_sets, IT* out_col_idxs, VT* out_values);  \
+    int gkob200_csr_convert_to_hybrid_##V##_##I(void* stream, int64_t n, const IT* row_ptrs,                    \
+                                                const IT* col_idxs, const VT* values,                          \
+                                                const int64_t* coo_row_ptrs, int64_t ell_stride,               \
+                                                int64_t ell_width, IT* ell_col_idxs, VT* ell_values,           \
+                                                IT* coo_row_idxs, IT* coo_col_idxs, VT* coo_values);
+GKOB200_DECL_CONV_VI(f64, double, i32, int32_t)
+GKOB200_DECL_CONV_VI(f32, float, i32, int32_t)
+GKOB200_DECL_CONV_VI(f64, double, i64, int64_t)
+GKOB200_DECL_CONV_VI(f32, float, i64, int64_t)
+
+/* ------------------------------------------------------------------------- *
  * Dense BLAS-1  [ref: core/matrix/dense_kernels.hpp; oracle
  * reference/matrix/dense_kernels.cpp:158-378; replaced
  * common/unified/matrix/dense_kernels.cpp:58-466 + cuda/matrix/dense_kernels.cu:76-149]

@@ -139,3 +139,160 @@ def ref_solve(rp, ci, va, b, x0, solver="cg", fmt="csr", hybrid_limit=-1, precon
 
 def ref_threads():
     return int(ref().ref_num_threads())
+
+
+# ---- formats: plain-C oracle ------------------------------------------------
+def _b2(b):
+    b2 = np.ascontiguousarray(b.reshape(len(b), -1))
+    return b2, b2.shape[1]
+
+
+def csr_to_coo(rp, ci, va):
+    I = _i(rp.dtype)
+    rows = np.empty_like(ci)
+    getattr(lib(), f"oracle_convert_ptrs_to_idxs_{I}")(P(rp), i64(len(rp) - 1), P(rows))
+    return rows, ci.copy(), va.copy()
+
+
+def max_row_nnz(rp):
+    fn = getattr(lib(), f"oracle_compute_max_row_nnz_{_i(rp.dtype)}")
+    fn.restype = C.c_uint64
+    return int(fn(P(rp), i64(len(rp) - 1)))
+
+
+def csr_to_ell(rp, ci, va):
+    n = len(rp) - 1
+    width, stride = max_row_nnz(rp), n
+    cols = np.empty(width * stride, dtype=ci.dtype)
+    vals = np.empty(width * stride, dtype=va.dtype)
+    getattr(lib(), f"oracle_csr_to_ell_{_i(rp.dtype)}_{_v(va.dtype)}")(i64(n), P(rp), P(ci), P(va), i64(width),
+                                                                        i64(stride), P(cols), P(vals))
+    return width, stride, cols, vals
+
+
+def slice_sets(rp, slice_size=64, stride_factor=1):
+    n = len(rp) - 1
+    ns = -(-n // slice_size)
+    sets = np.zeros(ns + 1, dtype=np.uint64)
+    lens = np.zeros(ns, dtype=np.uint64)
+    getattr(lib(), f"oracle_compute_slice_sets_{_i(rp.dtype)}")(P(rp), i64(n), i64(slice_size), i64(stride_factor),
+                                                                 P(sets), P(lens))
+    return sets, lens
+
+
+def csr_to_sellp(rp, ci, va, slice_size=64, stride_factor=1):
+    n = len(rp) - 1
+    sets, lens = slice_sets(rp, slice_size, stride_factor)
+    total = int(sets[-1]) * slice_size
+    # rows >= n of the last (partial) slice are never written by the reference kernel
+    cols = np.zeros(total, dtype=ci.dtype)
+    vals = np.zeros(total, dtype=va.dtype)
+    getattr(lib(), f"oracle_csr_to_sellp_{_i(rp.dtype)}_{_v(va.dtype)}")(i64(n), P(rp), P(ci), P(va), i64(slice_size),
+                                                                          P(sets), P(cols), P(vals))
+    return sets, lens, cols, vals
+
+
+HYB_KINDS = {"column_limit": 0, "imbalance_limit": 1, "imbalance_bounded_limit": 2, "minimal_storage_limit": 3,
+             "automatic": 4}
+
+
+def hybrid_ell_width(rp, n_cols, kind="automatic", param=0, percent=0.8, ratio=0.0001):
+    n = len(rp) - 1
+    sizes = np.diff(rp).astype(np.uint64)
+    fn = lib().oracle_hybrid_ell_width
+    fn.restype = C.c_uint64
+    return int(fn(P(sizes), i64(n), HYB_KINDS[kind], C.c_uint64(param), f64(percent), f64(ratio), i64(n_cols)))
+
+
+def csr_to_hybrid(rp, ci, va, n_cols, kind="automatic", param=0, percent=0.8, ratio=0.0001):
+    n = len(rp) - 1
+    if kind == "minimal_storage_limit":
+        percent = ci.itemsize / (va.itemsize + 2 * ci.itemsize)
+        kind_ = "imbalance_limit"
+    else:
+        kind_ = kind
+    w = hybrid_ell_width(rp, n_cols, kind_, param, percent, ratio)
+    sizes = np.diff(rp).astype(np.uint64)
+    coo_ptrs = np.zeros(n + 1, dtype=np.int64)
+    lib().oracle_hybrid_compute_coo_row_ptrs(P(sizes), i64(n), C.c_uint64(w), P(coo_ptrs))
+    coo_nnz = int(coo_ptrs[n])
+    ecols, evals = np.empty(w * n, dtype=ci.dtype), np.empty(w * n, dtype=va.dtype)
+    crows, ccols = np.empty(coo_nnz, dtype=ci.dtype), np.empty(coo_nnz, dtype=ci.dtype)
+    cvals = np.empty(coo_nnz, dtype=va.dtype)
+    getattr(lib(), f"oracle_csr_to_hybrid_{_i(rp.dtype)}_{_v(va.dtype)}")(
+        i64(n), P(rp), P(ci), P(va), P(coo_ptrs), i64(n), i64(w), P(ecols), P(evals), P(crows), P(ccols), P(cvals))
+    return dict(ell_width=w, ell_stride=n, ell_cols=ecols, ell_vals=evals, coo_rows=crows, coo_cols=ccols,
+                coo_vals=cvals, coo_row_ptrs=coo_ptrs)
+
+
+def ell_spmv(n, stride, width, cols, vals, b, alpha=None, beta=None, c=None):
+    b2, k = _b2(b)
+    out = np.zeros((n, k), dtype=vals.dtype) if c is None else np.ascontiguousarray(c.reshape(n, -1)).copy()
+    adv = alpha is not None
+    getattr(lib(), f"oracle_ell_spmv_{_i(cols.dtype)}_{_v(vals.dtype)}")(
+        i64(n), i64(stride), i64(width), P(cols), P(vals), int(adv), _c(vals.dtype, alpha or 0), P(b2), i64(k), i64(k),
+        _c(vals.dtype, beta or 0), P(out), i64(k))
+    return out
+
+
+def sellp_spmv(n, slice_size, sets, lens, cols, vals, b, alpha=None, beta=None, c=None):
+    b2, k = _b2(b)
+    out = np.zeros((n, k), dtype=vals.dtype) if c is None else np.ascontiguousarray(c.reshape(n, -1)).copy()
+    adv = alpha is not None
+    getattr(lib(), f"oracle_sellp_spmv_{_i(cols.dtype)}_{_v(vals.dtype)}")(
+        i64(n), i64(slice_size), P(sets), P(lens), P(cols), P(vals), int(adv), _c(vals.dtype, alpha or 0), P(b2),
+        i64(k), i64(k), _c(vals.dtype, beta or 0), P(out), i64(k))
+    return out
+
+
+def coo_spmv2(rows, cols, vals, b, c, alpha=None):
+    """c += [alpha] A b (returns the updated copy of c)."""
+    b2, k = _b2(b)
+    out = np.ascontiguousarray(c.reshape(len(c), -1)).copy()
+    getattr(lib(), f"oracle_coo_spmv2_{_i(cols.dtype)}_{_v(vals.dtype)}")(
+        i64(len(vals)), P(rows), P(cols), P(vals), int(alpha is not None), _c(vals.dtype, alpha or 0), P(b2), i64(k),
+        i64(k), P(out), i64(k))
+    return out
+
+
+def prefix_sum(a):
+    name = {np.dtype(np.int32): "i32", np.dtype(np.int64): "i64", np.dtype(np.uint64): "u64"}[a.dtype]
+    out = a.copy()
+    getattr(lib(), f"oracle_prefix_sum_{name}")(P(out), i64(len(out)))
+    return out
+
+
+# ---- formats: compiled reference ---------------------------------------------
+def ref_convert(rp, ci, va, n_cols, fmt, hyb_kind="automatic", hyb_param=0, percent=0.8, ratio=0.0001, slice_size=64,
+                stride_factor=1):
+    """Csr::convert_to(<fmt>) on the ReferenceExecutor; returns a dict of the result arrays."""
+    r = ref()
+    n, nnz = len(rp) - 1, len(ci)
+    V, I = _v(va.dtype), _i(rp.dtype)
+    cap = max(1, (n + 64) * (int(np.diff(rp).max()) if n else 1) + 64 * 64)
+    meta = np.zeros(4, dtype=np.int64)
+    ia, ib = np.empty(cap, dtype=ci.dtype), np.empty(cap, dtype=ci.dtype)
+    ov = np.empty(cap, dtype=va.dtype)
+    ua, ub = np.zeros(n + 2, dtype=np.uint64), np.zeros(n + 2, dtype=np.uint64)
+    cr, cc, cv = np.empty(cap, dtype=ci.dtype), np.empty(cap, dtype=ci.dtype), np.empty(cap, dtype=va.dtype)
+    fn = getattr(r, f"ref_convert_{V}_{I}")
+    fn.restype = i64
+    total = fn(FORMATS[fmt], HYB_KINDS[hyb_kind], i64(hyb_param), f64(percent), f64(ratio), i64(slice_size),
+               i64(stride_factor), i64(n), i64(n_cols), i64(nnz), P(rp), P(ci), P(va), P(meta), P(ia), P(ib), P(ov),
+               P(ua), P(ub), P(cr), P(cc), P(cv), i64(cap))
+    if total < 0:
+        raise RuntimeError(f"ref_convert rc={total}")
+    if fmt == "ell":
+        return dict(width=int(meta[0]), stride=int(meta[1]), cols=ia[:total].copy(), vals=ov[:total].copy())
+    if fmt == "sellp":
+        ns = int(meta[1])
+        return dict(total_cols=int(meta[0]), slice_sets=ua[:ns + 1].copy(), slice_lengths=ub[:ns].copy(),
+                    cols=ia[:total].copy(), vals=ov[:total].copy())
+    if fmt == "coo":
+        return dict(rows=ia[:total].copy(), cols=ib[:total].copy(), vals=ov[:total].copy())
+    if fmt == "hybrid":
+        cn = int(meta[2])
+        return dict(ell_width=int(meta[0]), ell_stride=int(meta[1]), ell_cols=ia[:total].copy(),
+                    ell_vals=ov[:total].copy(), coo_rows=cr[:cn].copy(), coo_cols=cc[:cn].copy(),
+                    coo_vals=cv[:cn].copy())
+    raise ValueError(fmt)

@@ -14,6 +14,79 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* ---- integer kernels ------------------------------------------------------ */
+#define ORACLE_INDEX_UNSIGNED
+#define IT uint64_t
+#define ISFX(name) name##_u64
+#include "oracle_index.inc"
+#undef IT
+#undef ISFX
+#undef ORACLE_INDEX_UNSIGNED
+#define IT int32_t
+#define ISFX(name) name##_i32
+#include "oracle_index.inc"
+#undef IT
+#undef ISFX
+#define IT int64_t
+#define ISFX(name) name##_i64
+#include "oracle_index.inc"
+#undef IT
+#undef ISFX
+
+static int cmp_u64(const void* a, const void* b)
+{
+    const uint64_t x = *(const uint64_t*)a, y = *(const uint64_t*)b;
+    return x < y ? -1 : x > y;
+}
+/* Hybrid strategies  [include/ginkgo/core/matrix/hybrid.hpp:178-380]: ELL width from the
+ * SORTED row lengths.  kind 0 column_limit(param_i), 1 imbalance_limit(percent),
+ * 2 imbalance_bounded_limit(percent, ratio), 3 minimal_storage_limit (percent given by
+ * the caller = sizeof(I)/(sizeof(V)+2 sizeof(I))), 4 automatic = bounded(1/3, 0.001).
+ * Also applies Csr::convert_to(Hybrid)'s clamp ell_lim <= num_cols (core/matrix/csr.cpp:300-303). */
+uint64_t oracle_hybrid_ell_width(const uint64_t* row_nnz, int64_t n, int kind, uint64_t param_i, double percent,
+                                 double ratio, int64_t num_cols)
+{
+    uint64_t res = 0;
+    if (kind == 0) {
+        res = param_i;
+    } else {
+        if (kind == 4) {
+            percent = 1.0 / 3.0;
+            ratio = 0.001;
+        }
+        if (percent > 1.0) percent = 1.0;
+        if (percent < 0.0) percent = 0.0;
+        if (n == 0) {
+            res = 0;
+        } else {
+            uint64_t* tmp = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)n);
+            memcpy(tmp, row_nnz, sizeof(uint64_t) * (size_t)n);
+            qsort(tmp, (size_t)n, sizeof(uint64_t), cmp_u64);
+            if (percent < 1) {
+                res = tmp[(uint64_t)(n * percent)];
+            } else {
+                res = tmp[n - 1];
+            }
+            free(tmp);
+        }
+        if (kind == 2 || kind == 4) {
+            const uint64_t bound = (uint64_t)(n * ratio);
+            if (bound < res) res = bound;
+        }
+    }
+    if (res > (uint64_t)num_cols) res = (uint64_t)num_cols;
+    return res;
+}
+/* [common/unified/matrix/hybrid_kernels.cpp:51-64] */
+void oracle_hybrid_compute_coo_row_ptrs(const uint64_t* row_nnz, int64_t n, uint64_t ell_lim, int64_t* coo_row_ptrs)
+{
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t d = (int64_t)row_nnz[i] - (int64_t)ell_lim;
+        coo_row_ptrs[i] = d > 0 ? d : 0;
+    }
+    oracle_prefix_sum_i64(coo_row_ptrs, n + 1);
+}
+
 #define V double
 #define SFX(name) name##_f64
 #define SQRT sqrt

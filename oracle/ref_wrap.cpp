@@ -219,6 +219,79 @@ int64_t solve_impl(int exec_kind, int solver_kind, int format, int64_t hybrid_li
     }
 }
 
+// ---- format conversions through the real reference executor ----------------------
+template <typename V, typename I>
+int64_t convert_impl(int format, int hyb_kind, int64_t hyb_param, double percent, double ratio, int64_t slice_size,
+                     int64_t stride_factor, int64_t n_rows, int64_t n_cols, int64_t nnz, const I* rp, const I* ci,
+                     const V* va, int64_t* meta, I* out_idx_a, I* out_idx_b, V* out_vals, uint64_t* out_u64_a,
+                     uint64_t* out_u64_b, I* coo_rows, I* coo_cols, V* coo_vals, int64_t cap)
+{
+    try {
+        auto exec = gko::ReferenceExecutor::create();
+        auto csr = csr_view<V, I>(exec, n_rows, n_cols, nnz, rp, ci, va);
+        if (format == 1) {
+            auto m = gko::matrix::Ell<V, I>::create(exec);
+            csr->convert_to(m.get());
+            const int64_t total = m->get_num_stored_elements();
+            meta[0] = m->get_num_stored_elements_per_row();
+            meta[1] = m->get_stride();
+            if (total > cap) return -3;
+            std::copy_n(m->get_const_col_idxs(), total, out_idx_a);
+            std::copy_n(m->get_const_values(), total, out_vals);
+            return total;
+        } else if (format == 2) {
+            auto m = gko::matrix::Sellp<V, I>::create(exec, gko::dim<2>{}, slice_size, stride_factor, 0);
+            csr->convert_to(m.get());
+            const int64_t ns = gko::ceildiv(n_rows, slice_size);
+            const int64_t total = m->get_num_stored_elements();
+            meta[0] = m->get_total_cols();
+            meta[1] = ns;
+            if (total > cap) return -3;
+            std::copy_n(m->get_const_slice_sets(), ns + 1, out_u64_a);
+            std::copy_n(m->get_const_slice_lengths(), ns, out_u64_b);
+            std::copy_n(m->get_const_col_idxs(), total, out_idx_a);
+            std::copy_n(m->get_const_values(), total, out_vals);
+            return total;
+        } else if (format == 3) {
+            auto m = gko::matrix::Coo<V, I>::create(exec);
+            csr->convert_to(m.get());
+            if (nnz > cap) return -3;
+            std::copy_n(m->get_const_row_idxs(), nnz, out_idx_a);
+            std::copy_n(m->get_const_col_idxs(), nnz, out_idx_b);
+            std::copy_n(m->get_const_values(), nnz, out_vals);
+            return nnz;
+        } else if (format == 4) {
+            using Hyb = gko::matrix::Hybrid<V, I>;
+            std::shared_ptr<typename Hyb::strategy_type> strat;
+            switch (hyb_kind) {
+            case 0: strat = std::make_shared<typename Hyb::column_limit>(static_cast<gko::size_type>(hyb_param)); break;
+            case 1: strat = std::make_shared<typename Hyb::imbalance_limit>(percent); break;
+            case 2: strat = std::make_shared<typename Hyb::imbalance_bounded_limit>(percent, ratio); break;
+            case 3: strat = std::make_shared<typename Hyb::minimal_storage_limit>(); break;
+            default: strat = std::make_shared<typename Hyb::automatic>(); break;
+            }
+            auto m = Hyb::create(exec, strat);
+            csr->convert_to(m.get());
+            const int64_t ell_total = m->get_ell_num_stored_elements();
+            const int64_t coo_nnz = m->get_coo_num_stored_elements();
+            meta[0] = m->get_ell_num_stored_elements_per_row();
+            meta[1] = m->get_ell_stride();
+            meta[2] = coo_nnz;
+            if (ell_total > cap || coo_nnz > cap) return -3;
+            std::copy_n(m->get_const_ell_col_idxs(), ell_total, out_idx_a);
+            std::copy_n(m->get_const_ell_values(), ell_total, out_vals);
+            std::copy_n(m->get_const_coo_row_idxs(), coo_nnz, coo_rows);
+            std::copy_n(m->get_const_coo_col_idxs(), coo_nnz, coo_cols);
+            std::copy_n(m->get_const_coo_values(), coo_nnz, coo_vals);
+            return ell_total;
+        }
+        return -2;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "ref_wrap: %s\n", e.what());
+        return -1;
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -245,6 +318,20 @@ void ref_set_num_threads(int n) { omp_set_num_threads(n); }
                                   precond_block, max_iters, factor, baseline, krylov_dim, nrhs, b, x, hist,      \
                                   hist_cap, hist_len, seconds);                                                  \
     }
+#define REF_CONVERT(V, VT, I, IT)                                                                                \
+    int64_t ref_convert_##V##_##I(int format, int hyb_kind, int64_t hyb_param, double percent, double ratio,     \
+                                  int64_t slice_size, int64_t stride_factor, int64_t n_rows, int64_t n_cols,     \
+                                  int64_t nnz, const IT* rp, const IT* ci, const VT* va, int64_t* meta,          \
+                                  IT* out_idx_a, IT* out_idx_b, VT* out_vals, uint64_t* out_u64_a,               \
+                                  uint64_t* out_u64_b, IT* coo_rows, IT* coo_cols, VT* coo_vals, int64_t cap)    \
+    {                                                                                                            \
+        return convert_impl<VT, IT>(format, hyb_kind, hyb_param, percent, ratio, slice_size, stride_factor,      \
+                                    n_rows, n_cols, nnz, rp, ci, va, meta, out_idx_a, out_idx_b, out_vals,       \
+                                    out_u64_a, out_u64_b, coo_rows, coo_cols, coo_vals, cap);                    \
+    }
+REF_CONVERT(f64, double, i32, int32_t)
+REF_CONVERT(f32, float, i32, int32_t)
+REF_CONVERT(f64, double, i64, int64_t)
 REF_SPMV(f64, double, i32, int32_t)
 REF_SPMV(f32, float, i32, int32_t)
 REF_SPMV(f64, double, i64, int64_t)

@@ -89,6 +89,29 @@ def declare(lib):
         d(f"gkob200_jacobi_simple_scalar_apply_{V}", [vp, i64, i64, vp, vp, i64, vp, i64])
         d(f"gkob200_jacobi_scalar_apply_{V}", [vp, i64, i64, vp, vp, vp, i64, vp, vp, i64])
     d("gkob200_set_all_statuses", [vp, i64, u8, C.c_int, vp])
+    # formats
+    d("gkob200_coo_spmv_workspace_bytes", [i64, C.c_int], sz)
+    for V in VT:
+        for I in ("i32", "i64"):
+            d(f"gkob200_ell_spmv_{V}_{I}", [vp, i64, i64, i64, i64, vp, vp, vp, i64, i64, vp, vp, vp, i64])
+            d(f"gkob200_sellp_spmv_{V}_{I}", [vp, i64, i64, i64, vp, vp, vp, vp, vp, i64, i64, vp, vp, vp, i64])
+            d(f"gkob200_coo_spmv_{V}_{I}", [vp, i64, i64, i64, vp, vp, vp, vp, i64, i64, vp, vp, vp, i64, vp, sz])
+            d(f"gkob200_coo_spmv2_{V}_{I}", [vp, i64, i64, i64, vp, vp, vp, vp, i64, i64, vp, vp, i64, vp, sz])
+            d(f"gkob200_csr_convert_to_ell_{V}_{I}", [vp, i64, vp, vp, vp, i64, i64, vp, vp])
+            d(f"gkob200_csr_convert_to_sellp_{V}_{I}", [vp, i64, vp, vp, vp, i64, vp, vp, vp])
+            d(f"gkob200_csr_convert_to_hybrid_{V}_{I}", [vp, i64, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, vp])
+    # integer kernels
+    d("gkob200_prefix_sum_workspace_bytes", [i64], sz)
+    for T in ("i32", "i64", "u64"):
+        d(f"gkob200_prefix_sum_{T}", [vp, vp, i64, vp, sz])
+    d("gkob200_hybrid_compute_coo_row_ptrs", [vp, vp, i64, u64, vp, vp, sz])
+    for I in ("i32", "i64"):
+        d(f"gkob200_convert_ptrs_to_idxs_{I}", [vp, vp, i64, vp])
+        d(f"gkob200_convert_idxs_to_ptrs_{I}", [vp, vp, i64, i64, vp])
+        d(f"gkob200_convert_ptrs_to_sizes_{I}", [vp, vp, i64, vp])
+        d(f"gkob200_compute_max_row_nnz_{I}", [vp, vp, i64, vp])
+        d(f"gkob200_sellp_compute_slice_sets_{I}", [vp, vp, i64, i64, i64, vp, vp, vp, sz])
+        d(f"gkob200_row_len_histogram_{I}", [vp, vp, i64, u64, u64, C.c_int, vp])
     # generators (host)
     d("gkob200_gen_stencil_nnz", [C.c_int, i64, i64, i64, i64, i64], i64)
     for V in VT:

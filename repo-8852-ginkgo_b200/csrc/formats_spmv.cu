@@ -1,0 +1,489 @@
+// formats_spmv.cu — ELL, SELL-P and COO SpMV / SpMM for sm_100a.
+//
+// Replaces gko::kernels::cuda::{ell,sellp,coo}::{spmv,advanced_spmv,spmv2,advanced_spmv2}
+// (reference cuda/matrix/{ell,sellp,coo}_kernels.cu; device code
+// common/cuda_hip/matrix/{ell,sellp,coo}_kernels.hpp.inc) and follows the arithmetic of
+// the oracle reference/matrix/{ell,sellp,coo}_kernels.cpp.
+//
+// ELL / SELL-P: one thread per row; both formats store a row's entries strided by the
+// (slice) height, so the col/val streams of a warp are fully coalesced 128/256-byte
+// lines and, for banded matrices, so are the gathers x[col].  A thread issues a batch
+// of independent loads before it starts adding, and adds in storage order with a
+// rounded product + rounded sum: bit-identical to the reference executor.  Padding
+// entries (col == -1) are skipped like the reference does.
+//
+// Multi-RHS (SpMM): a warp owns 32 rows x 32 right-hand sides; lane = RHS column, the
+// (col,val) of the 32 rows are loaded coalesced once per stored column and broadcast
+// with shuffles, every b / c access is one full contiguous line.
+//
+// COO (accumulating spmv2, row-sorted): nnz are split evenly over CTAs and threads;
+// products are staged coalesced into shared memory, each thread reduces its run of
+// entries, row pieces are stitched in thread order inside the CTA and per-CTA carries
+// by a small fix-up kernel.  No atomics (the reference's coo kernel uses atomic_add:
+// common/cuda_hip/matrix/coo_kernels.hpp.inc:54-218), deterministic.
+//
+// Algorithmic bytes: ELL n*w*(V+I) + (n_cols+n)*k*V;
+// SELL-P S*(V+I) + (ns+1)*8 + (n_cols+n)*k*V; COO nnz*(V+2I) + n_cols*k*V + 2*n*k*V.
+#include "internal.h"
+
+namespace gkob200 {
+namespace {
+
+constexpr int kBatch = 9;
+
+// ---------------------------------------------------------------------------
+// thread-per-row kernel shared by ELL and SELL-P.  `Fmt` gives, for a row, the
+// position of its first stored entry, the distance between consecutive entries
+// and the number of stored entries.
+// ---------------------------------------------------------------------------
+struct EllFmt {
+    int64_t stride, width;
+    __device__ __forceinline__ void row(int64_t r, int64_t& first, int64_t& step, int64_t& len) const
+    {
+        first = r;
+        step = stride;
+        len = width;
+    }
+};
+struct SellpFmt {
+    int64_t slice_size;
+    const uint64_t* slice_sets;
+    const uint64_t* slice_lengths;
+    __device__ __forceinline__ void row(int64_t r, int64_t& first, int64_t& step, int64_t& len) const
+    {
+        const int64_t slice = r / slice_size;
+        first = static_cast<int64_t>(slice_sets[slice]) * slice_size + (r - slice * slice_size);
+        step = slice_size;
+        len = static_cast<int64_t>(slice_lengths[slice]);
+    }
+};
+
+template <typename V, typename I, typename Fmt, bool Advanced, bool Fused>
+__global__ void __launch_bounds__(256)
+    strided_spmv(int64_t n_rows, Fmt fmt, const I* __restrict__ cols, const V* __restrict__ vals,
+                 const V* __restrict__ b, int64_t b_stride, const V* __restrict__ alpha_p,
+                 const V* __restrict__ beta_p, V* __restrict__ c, int64_t c_stride, SpmvFusion<V> fu)
+{
+    if (Fused && fu.skip && *fu.skip) return;
+    const int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    const bool live = r < n_rows;
+    V acc = V(0), alpha = V(1);
+    if (live) {
+        int64_t first, step, len;
+        fmt.row(r, first, step, len);
+        if (Advanced) {
+            alpha = *alpha_p;
+            acc = mul_rn(c[r * c_stride], *beta_p);
+        }
+        for (int64_t i = 0; i < len; i += kBatch) {
+            V v[kBatch], xv[kBatch];
+            I col[kBatch];
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const bool in = i + u < len;
+                col[u] = in ? cols[first + (i + u) * step] : I(-1);
+                v[u] = in ? vals[first + (i + u) * step] : V(0);
+            }
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u)
+                xv[u] = col[u] != I(-1) ? ldg(b + static_cast<int64_t>(col[u]) * b_stride) : V(0);
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                if (col[u] != I(-1))
+                    acc = Advanced ? add_rn(acc, mul_rn(mul_rn(alpha, v[u]), xv[u]))
+                                   : add_rn(acc, mul_rn(v[u], xv[u]));
+            }
+        }
+        c[r * c_stride] = acc;
+    }
+    if (Fused && fu.out) {
+        V t[1] = {live ? acc * fu.w[r] : V(0)};
+        V* out = fu.out;
+        grid_reduce<1>(t, ws_partials<V>(fu.ws), ws_ticket(fu.ws), [out](V(&tot)[1]) { out[0] = tot[0]; });
+    }
+}
+
+// SpMM: warp = 32 rows x 32 RHS columns (lane = RHS column)
+template <typename V, typename I, typename Fmt, bool Advanced>
+__global__ void __launch_bounds__(128)
+    strided_spmm(int64_t n_rows, Fmt fmt, const I* __restrict__ cols, const V* __restrict__ vals,
+                 const V* __restrict__ b, int64_t b_stride, int64_t nrhs, const V* __restrict__ alpha_p,
+                 const V* __restrict__ beta_p, V* __restrict__ c, int64_t c_stride)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+    const int64_t row0 = warp * 32;
+    if (row0 >= n_rows) return;
+    const int64_t my_row = row0 + lane;  // the row whose (col,val) this lane fetches
+    int64_t first = 0, step = 0, len = 0;
+    if (my_row < n_rows) fmt.row(my_row, first, step, len);
+    int64_t max_len = len;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) max_len = max(max_len, __shfl_xor_sync(0xffffffffu, max_len, o));
+    const int nr = static_cast<int>(min(static_cast<int64_t>(32), n_rows - row0));
+    V alpha = V(1), beta = V(0);
+    if (Advanced) {
+        alpha = *alpha_p;
+        beta = *beta_p;
+    }
+    for (int64_t j0 = 0; j0 < nrhs; j0 += 32) {
+        const int64_t j = j0 + lane;
+        const bool jl = j < nrhs;
+        V acc[32];
+#pragma unroll
+        for (int r = 0; r < 32; ++r)
+            acc[r] = (Advanced && jl && r < nr) ? mul_rn(c[(row0 + r) * c_stride + j], beta) : V(0);
+        for (int64_t i = 0; i < max_len; ++i) {
+            const bool in = i < len;
+            const I mycol = in ? cols[first + i * step] : I(-1);
+            V myval = in ? vals[first + i * step] : V(0);
+            if (Advanced) myval = mul_rn(alpha, myval);
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                const I col = __shfl_sync(0xffffffffu, mycol, r);
+                const V v = __shfl_sync(0xffffffffu, myval, r);
+                if (col != I(-1) && jl) acc[r] = add_rn(acc[r], mul_rn(v, ldg(b + static_cast<int64_t>(col) * b_stride + j)));
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 32; ++r)
+            if (jl && r < nr) c[(row0 + r) * c_stride + j] = acc[r];
+    }
+}
+
+template <typename V, typename I, typename Fmt>
+int strided_launch(cudaStream_t s, int64_t n_rows, Fmt fmt, const I* cols, const V* vals, const V* b,
+                   int64_t b_stride, int64_t nrhs, const V* alpha, const V* beta, V* c, int64_t c_stride,
+                   const SpmvFusion<V>* fusion)
+{
+    const bool adv = alpha != nullptr;
+    if (nrhs > 1) {
+        if (fusion && fusion->out) return GKOB200_EUNSUPPORTED;
+        const unsigned grid = static_cast<unsigned>(ceildiv(ceildiv(n_rows, 32), 4));
+        if (adv)
+            strided_spmm<V, I, Fmt, true><<<grid, 128, 0, s>>>(n_rows, fmt, cols, vals, b, b_stride, nrhs, alpha, beta, c, c_stride);
+        else
+            strided_spmm<V, I, Fmt, false><<<grid, 128, 0, s>>>(n_rows, fmt, cols, vals, b, b_stride, nrhs, alpha, beta, c, c_stride);
+        GKOB200_CHECK_LAUNCH();
+        return 0;
+    }
+    SpmvFusion<V> fu;
+    if (fusion) fu = *fusion;
+    const bool fused = fusion != nullptr;
+    const unsigned grid = static_cast<unsigned>(ceildiv(n_rows, 256));
+    if (fused && fu.out && static_cast<int64_t>(grid) > fu.ws_blocks) return GKOB200_EWORKSPACE;
+#define GKOB200_ST(ADV, FUSED) \
+    strided_spmv<V, I, Fmt, ADV, FUSED><<<grid, 256, 0, s>>>(n_rows, fmt, cols, vals, b, b_stride, alpha, beta, c, c_stride, fu)
+    if (adv && fused) GKOB200_ST(true, true);
+    else if (adv) GKOB200_ST(true, false);
+    else if (fused) GKOB200_ST(false, true);
+    else GKOB200_ST(false, false);
+#undef GKOB200_ST
+    GKOB200_CHECK_LAUNCH();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// COO  c += [alpha] A b   (row-sorted entries)
+// ---------------------------------------------------------------------------
+constexpr int kCooThreads = 128;
+constexpr int kCooItems = 8;
+constexpr int kCooTile = kCooThreads * kCooItems;
+
+template <typename V, typename I, bool Advanced>
+__global__ void __launch_bounds__(kCooThreads)
+    coo_spmv2(int64_t nnz, const I* __restrict__ rows, const I* __restrict__ cols, const V* __restrict__ vals,
+              const V* __restrict__ b, int64_t b_stride, int64_t j, const V* __restrict__ alpha_p,
+              V* __restrict__ c, int64_t c_stride, int64_t* __restrict__ carry_row, V* __restrict__ carry_val)
+{
+    // stride kCooItems+1 keeps the per-thread sequential walks bank-conflict free
+    __shared__ V s_prod[kCooThreads * (kCooItems + 1)];
+    __shared__ I s_row[kCooThreads * (kCooItems + 1)];
+    __shared__ I s_first_row[kCooThreads], s_last_row[kCooThreads];
+    __shared__ V s_first_sum[kCooThreads], s_last_sum[kCooThreads];
+    __shared__ bool s_single[kCooThreads];
+
+    const int tid = threadIdx.x;
+    const int64_t k0 = static_cast<int64_t>(blockIdx.x) * kCooTile;
+    const int len = static_cast<int>(min(static_cast<int64_t>(kCooTile), nnz - k0));
+    V alpha = V(1);
+    if (Advanced) alpha = *alpha_p;
+    for (int k = tid; k < len; k += kCooThreads) {
+        const V v = vals[k0 + k];
+        const V xv = ldg(b + static_cast<int64_t>(cols[k0 + k]) * b_stride + j);
+        const int pos = k + k / kCooItems;
+        s_prod[pos] = Advanced ? mul_rn(mul_rn(alpha, v), xv) : mul_rn(v, xv);
+        s_row[pos] = rows[k0 + k];
+    }
+    __syncthreads();
+    // thread t owns entries [t*kCooItems, ...): sequential, in storage order.
+    // Rows that start AND end inside the thread's run are complete: added to c directly
+    // (no other thread touches them).  The first and last row of the run may continue
+    // in neighbouring threads: kept as (row, sum) pieces.
+    const int begin = tid * kCooItems, end = min(begin + kCooItems, len);
+    I first_row = I(-1), last_row = I(-1);
+    V first_sum = V(0), last_sum = V(0);
+    bool single = true;
+    if (begin < end) {
+        const int base = begin + tid;  // padded position of entry `begin`
+        I cur = s_row[base];
+        V sum = s_prod[base];
+        first_row = cur;
+        for (int k = 1; k < end - begin; ++k) {
+            const I r = s_row[base + k];
+            const V p = s_prod[base + k];
+            if (r == cur) {
+                sum = add_rn(sum, p);
+            } else {
+                if (single) {
+                    first_sum = sum;
+                    single = false;
+                } else {
+                    c[static_cast<int64_t>(cur) * c_stride + j] = add_rn(c[static_cast<int64_t>(cur) * c_stride + j], sum);
+                }
+                cur = r;
+                sum = p;
+            }
+        }
+        last_row = cur;
+        last_sum = sum;
+        if (single) first_sum = sum;
+    }
+    s_first_row[tid] = first_row;
+    s_last_row[tid] = last_row;
+    s_first_sum[tid] = first_sum;
+    s_last_sum[tid] = last_sum;
+    s_single[tid] = single;
+    __syncthreads();
+    // Stitch: a "piece list" in thread order: for each thread, its first piece and (if
+    // not single) its last piece.  The leader of each run of equal rows adds the run in
+    // order.  Runs touching the tile's first or last entry are exported as carries
+    // (the neighbouring tiles may continue the same row); the others go to c.
+    if (begin < end) {
+        // does my first piece start a run?  (previous piece = last piece of thread tid-1)
+        const bool starts = tid == 0 || s_last_row[tid - 1] != first_row;
+        if (starts) {
+            V run = first_sum;
+            bool open = single;  // run continues into following threads only if I am a single-row thread
+            int t = tid + 1;
+            while (open && t < kCooThreads && s_first_row[t] == first_row) {
+                run = add_rn(run, s_first_sum[t]);
+                open = s_single[t];
+                ++t;
+            }
+            const bool touches_begin = tid == 0;
+            const bool touches_end = open && (t >= kCooThreads || s_first_row[t] == I(-1));
+            if (touches_begin) {
+                carry_row[2 * blockIdx.x] = first_row;
+                carry_val[2 * blockIdx.x] = run;
+                if (touches_end) {  // the whole tile is one row: second slot empty
+                    carry_row[2 * blockIdx.x + 1] = -1;
+                    carry_val[2 * blockIdx.x + 1] = V(0);
+                }
+            } else if (touches_end) {
+                carry_row[2 * blockIdx.x + 1] = first_row;
+                carry_val[2 * blockIdx.x + 1] = run;
+            } else {
+                c[static_cast<int64_t>(first_row) * c_stride + j] =
+                    add_rn(c[static_cast<int64_t>(first_row) * c_stride + j], run);
+            }
+        }
+        if (!single) {
+            // my last piece always starts a run (its row differs from my previous rows)
+            V run = last_sum;
+            bool open = true;
+            int t = tid + 1;
+            while (open && t < kCooThreads && s_first_row[t] == last_row) {
+                run = add_rn(run, s_first_sum[t]);
+                open = s_single[t];
+                ++t;
+            }
+            const bool touches_end = open && (t >= kCooThreads || s_first_row[t] == I(-1));
+            if (touches_end) {
+                carry_row[2 * blockIdx.x + 1] = last_row;
+                carry_val[2 * blockIdx.x + 1] = run;
+            } else {
+                c[static_cast<int64_t>(last_row) * c_stride + j] =
+                    add_rn(c[static_cast<int64_t>(last_row) * c_stride + j], run);
+            }
+        }
+    }
+}
+
+// carries: 2 slots per tile (first-row piece, last-row piece), in tile order; runs of
+// equal rows are added in order by their leader.  Deterministic, no atomics.
+template <typename V>
+__global__ void coo_fixup(int64_t n_slots, const int64_t* __restrict__ carry_row, const V* __restrict__ carry_val,
+                          V* __restrict__ c, int64_t c_stride, int64_t j)
+{
+    const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (t >= n_slots) return;
+    const int64_t row = carry_row[t];
+    if (row < 0) return;
+    // previous non-empty slot
+    int64_t p = t - 1;
+    while (p >= 0 && carry_row[p] < 0) --p;
+    if (p >= 0 && carry_row[p] == row) return;
+    V run = carry_val[t];
+    for (int64_t u = t + 1; u < n_slots; ++u) {
+        if (carry_row[u] < 0) continue;
+        if (carry_row[u] != row) break;
+        run = add_rn(run, carry_val[u]);
+    }
+    c[row * c_stride + j] = add_rn(c[row * c_stride + j], run);
+}
+
+template <typename V, typename I>
+int coo_spmv2_launch(cudaStream_t s, int64_t n_rows, int64_t nnz, const I* rows, const I* cols, const V* vals,
+                     const V* b, int64_t b_stride, int64_t nrhs, const V* alpha, V* c, int64_t c_stride,
+                     void* workspace, size_t workspace_bytes)
+{
+    if (nnz == 0 || nrhs == 0 || n_rows == 0) return 0;
+    const int64_t n_tiles = ceildiv(nnz, kCooTile);
+    const size_t need = gkob200_coo_spmv_workspace_bytes(nnz, sizeof(V));
+    if (!workspace || workspace_bytes < need) return GKOB200_EWORKSPACE;
+    int64_t* carry_row = reinterpret_cast<int64_t*>(workspace);
+    V* carry_val = reinterpret_cast<V*>(carry_row + 2 * n_tiles);
+    for (int64_t j = 0; j < nrhs; ++j) {
+        GKOB200_CUDA(cudaMemsetAsync(carry_row, 0xff, static_cast<size_t>(2 * n_tiles) * sizeof(int64_t), s));
+        if (alpha)
+            coo_spmv2<V, I, true><<<static_cast<unsigned>(n_tiles), kCooThreads, 0, s>>>(
+                nnz, rows, cols, vals, b, b_stride, j, alpha, c, c_stride, carry_row, carry_val);
+        else
+            coo_spmv2<V, I, false><<<static_cast<unsigned>(n_tiles), kCooThreads, 0, s>>>(
+                nnz, rows, cols, vals, b, b_stride, j, alpha, c, c_stride, carry_row, carry_val);
+        GKOB200_CHECK_LAUNCH();
+        coo_fixup<V><<<static_cast<unsigned>(ceildiv(2 * n_tiles, 256)), 256, 0, s>>>(2 * n_tiles, carry_row, carry_val, c,
+                                                                                   c_stride, j);
+        GKOB200_CHECK_LAUNCH();
+    }
+    return 0;
+}
+
+// c = beta * c (or 0) ahead of the accumulating COO kernel
+template <typename V>
+__global__ void scale_or_zero(int64_t n, int64_t k, V* c, int64_t cs, const V* beta)
+{
+    const int64_t total = n * k;
+    const V be = beta ? *beta : V(0);
+    for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
+         t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        V& v = c[(t / k) * cs + t % k];
+        v = beta ? mul_rn(v, be) : V(0);
+    }
+}
+
+}  // namespace
+
+// ---- C++ entry points used by matrix_apply.cu --------------------------------
+template <typename V, typename I>
+int ell_spmv_launch(cudaStream_t s, int64_t n_rows, int64_t stride, int64_t width, const I* cols, const V* vals,
+                    const V* b, int64_t b_stride, int64_t nrhs, const V* alpha, const V* beta, V* c,
+                    int64_t c_stride, const SpmvFusion<V>* fusion)
+{
+    if (n_rows < 0 || width < 0 || stride < n_rows || nrhs < 0 || (alpha == nullptr) != (beta == nullptr))
+        return GKOB200_EINVAL;
+    if (n_rows == 0 || nrhs == 0) return 0;
+    if (!c || (width > 0 && (!cols || !vals || !b))) return GKOB200_EINVAL;
+    return strided_launch<V, I>(s, n_rows, EllFmt{stride, width}, cols, vals, b, b_stride, nrhs, alpha, beta, c,
+                                c_stride, fusion);
+}
+
+template <typename V, typename I>
+int sellp_spmv_launch(cudaStream_t s, int64_t n_rows, int64_t slice_size, const uint64_t* slice_sets,
+                      const uint64_t* slice_lengths, const I* cols, const V* vals, const V* b, int64_t b_stride,
+                      int64_t nrhs, const V* alpha, const V* beta, V* c, int64_t c_stride,
+                      const SpmvFusion<V>* fusion)
+{
+    if (n_rows < 0 || slice_size <= 0 || nrhs < 0 || (alpha == nullptr) != (beta == nullptr)) return GKOB200_EINVAL;
+    if (n_rows == 0 || nrhs == 0) return 0;
+    if (!c || !slice_sets || !slice_lengths) return GKOB200_EINVAL;
+    return strided_launch<V, I>(s, n_rows, SellpFmt{slice_size, slice_sets, slice_lengths}, cols, vals, b, b_stride,
+                                nrhs, alpha, beta, c, c_stride, fusion);
+}
+
+template <typename V, typename I>
+int coo_spmv_launch(cudaStream_t s, int64_t n_rows, int64_t nnz, const I* rows, const I* cols, const V* vals,
+                    const V* b, int64_t b_stride, int64_t nrhs, const V* alpha, const V* beta, bool accumulate,
+                    V* c, int64_t c_stride, void* workspace, size_t workspace_bytes)
+{
+    if (n_rows < 0 || nnz < 0 || nrhs < 0) return GKOB200_EINVAL;
+    if (n_rows == 0 || nrhs == 0) return 0;
+    if (!c || (nnz > 0 && (!rows || !cols || !vals || !b))) return GKOB200_EINVAL;
+    if (!accumulate) {
+        // coo::spmv = fill(c, 0) + spmv2; advanced_spmv = scale(beta, c) + advanced_spmv2
+        // [reference/matrix/coo_kernels.cpp:62-89]
+        scale_or_zero<V><<<grid_for(n_rows * nrhs, 256, 8), 256, 0, s>>>(n_rows, nrhs, c, c_stride, beta);
+        GKOB200_CHECK_LAUNCH();
+    }
+    return coo_spmv2_launch<V, I>(s, n_rows, nnz, rows, cols, vals, b, b_stride, nrhs, alpha, c, c_stride, workspace,
+                                  workspace_bytes);
+}
+
+#define GKOB200_INST(V, I)                                                                                       \
+    template int ell_spmv_launch<V, I>(cudaStream_t, int64_t, int64_t, int64_t, const I*, const V*, const V*,    \
+                                       int64_t, int64_t, const V*, const V*, V*, int64_t, const SpmvFusion<V>*); \
+    template int sellp_spmv_launch<V, I>(cudaStream_t, int64_t, int64_t, const uint64_t*, const uint64_t*,       \
+                                         const I*, const V*, const V*, int64_t, int64_t, const V*, const V*, V*, \
+                                         int64_t, const SpmvFusion<V>*);                                         \
+    template int coo_spmv_launch<V, I>(cudaStream_t, int64_t, int64_t, const I*, const I*, const V*, const V*,   \
+                                       int64_t, int64_t, const V*, const V*, bool, V*, int64_t, void*, size_t);
+GKOB200_INST(double, int32_t)
+GKOB200_INST(float, int32_t)
+GKOB200_INST(double, int64_t)
+GKOB200_INST(float, int64_t)
+#undef GKOB200_INST
+
+}  // namespace gkob200
+
+using namespace gkob200;
+
+extern "C" {
+
+size_t gkob200_coo_spmv_workspace_bytes(int64_t nnz, int value_bytes)
+{
+    const int64_t n_tiles = ceildiv(nnz, kCooTile) + 1;
+    return static_cast<size_t>(2 * n_tiles) * (sizeof(int64_t) + static_cast<size_t>(value_bytes)) + 64;
+}
+
+#define GKOB200_DEF_FMT(V, VT, I, IT)                                                                          \
+    int gkob200_ell_spmv_##V##_##I(void* st, int64_t n_rows, int64_t n_cols, int64_t stride, int64_t width,     \
+                                   const IT* cols, const VT* vals, const VT* b, int64_t bs, int64_t nrhs,       \
+                                   const VT* alpha, const VT* beta, VT* c, int64_t cs)                          \
+    {                                                                                                          \
+        (void)n_cols;                                                                                          \
+        return ell_spmv_launch<VT, IT>(as_stream(st), n_rows, stride, width, cols, vals, b, bs, nrhs, alpha,    \
+                                       beta, c, cs, nullptr);                                                  \
+    }                                                                                                          \
+    int gkob200_sellp_spmv_##V##_##I(void* st, int64_t n_rows, int64_t n_cols, int64_t slice_size,              \
+                                     const uint64_t* slice_sets, const uint64_t* slice_lengths, const IT* cols, \
+                                     const VT* vals, const VT* b, int64_t bs, int64_t nrhs, const VT* alpha,    \
+                                     const VT* beta, VT* c, int64_t cs)                                         \
+    {                                                                                                          \
+        (void)n_cols;                                                                                          \
+        return sellp_spmv_launch<VT, IT>(as_stream(st), n_rows, slice_size, slice_sets, slice_lengths, cols,    \
+                                         vals, b, bs, nrhs, alpha, beta, c, cs, nullptr);                       \
+    }                                                                                                          \
+    int gkob200_coo_spmv_##V##_##I(void* st, int64_t n_rows, int64_t n_cols, int64_t nnz, const IT* rows,       \
+                                   const IT* cols, const VT* vals, const VT* b, int64_t bs, int64_t nrhs,       \
+                                   const VT* alpha, const VT* beta, VT* c, int64_t cs, void* ws, size_t wsb)    \
+    {                                                                                                          \
+        (void)n_cols;                                                                                          \
+        if ((alpha == nullptr) != (beta == nullptr)) return GKOB200_EINVAL;                                    \
+        return coo_spmv_launch<VT, IT>(as_stream(st), n_rows, nnz, rows, cols, vals, b, bs, nrhs, alpha, beta,  \
+                                       false, c, cs, ws, wsb);                                                 \
+    }                                                                                                          \
+    int gkob200_coo_spmv2_##V##_##I(void* st, int64_t n_rows, int64_t n_cols, int64_t nnz, const IT* rows,      \
+                                    const IT* cols, const VT* vals, const VT* b, int64_t bs, int64_t nrhs,      \
+                                    const VT* alpha, VT* c, int64_t cs, void* ws, size_t wsb)                   \
+    {                                                                                                          \
+        (void)n_cols;                                                                                          \
+        return coo_spmv_launch<VT, IT>(as_stream(st), n_rows, nnz, rows, cols, vals, b, bs, nrhs, alpha,        \
+                                       nullptr, true, c, cs, ws, wsb);                                         \
+    }
+GKOB200_DEF_FMT(f64, double, i32, int32_t)
+GKOB200_DEF_FMT(f32, float, i32, int32_t)
+GKOB200_DEF_FMT(f64, double, i64, int64_t)
+GKOB200_DEF_FMT(f32, float, i64, int64_t)
+
+}  // extern "C"

@@ -26,6 +26,21 @@ int csr_spmv_launch(cudaStream_t s, int64_t n_rows, int64_t n_cols, int64_t nnz,
                     int64_t max_block_nnz, void* workspace, size_t workspace_bytes,
                     const SpmvFusion<V>* fusion);
 
+template <typename V, typename I>
+int ell_spmv_launch(cudaStream_t s, int64_t n_rows, int64_t stride, int64_t width, const I* cols, const V* vals,
+                    const V* b, int64_t b_stride, int64_t nrhs, const V* alpha, const V* beta, V* c,
+                    int64_t c_stride, const SpmvFusion<V>* fusion);
+template <typename V, typename I>
+int sellp_spmv_launch(cudaStream_t s, int64_t n_rows, int64_t slice_size, const uint64_t* slice_sets,
+                      const uint64_t* slice_lengths, const I* cols, const V* vals, const V* b, int64_t b_stride,
+                      int64_t nrhs, const V* alpha, const V* beta, V* c, int64_t c_stride,
+                      const SpmvFusion<V>* fusion);
+// accumulate == true: c += [alpha] A b (spmv2); false: c = A b / c = alpha A b + beta c
+template <typename V, typename I>
+int coo_spmv_launch(cudaStream_t s, int64_t n_rows, int64_t nnz, const I* rows, const I* cols, const V* vals,
+                    const V* b, int64_t b_stride, int64_t nrhs, const V* alpha, const V* beta, bool accumulate,
+                    V* c, int64_t c_stride, void* workspace, size_t workspace_bytes);
+
 // y = A x (alpha == beta == nullptr) or y = alpha A x + beta y, any format.
 template <typename V>
 int matrix_apply(cudaStream_t s, const gkob200_matrix& A, const V* b, int64_t b_stride, int64_t nrhs,

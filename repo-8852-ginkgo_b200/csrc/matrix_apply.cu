@@ -15,7 +15,7 @@ bool matrix_apply_fuses_dot(const gkob200_matrix& A, int64_t nrhs)
                            : GKOB200_CSR_MERGE_PATH;
         return strategy == GKOB200_CSR_CLASSICAL;
     }
-    return false;
+    return A.format == GKOB200_FMT_ELL || A.format == GKOB200_FMT_SELLP;
 }
 
 template <typename V>
@@ -58,6 +58,60 @@ int matrix_apply(cudaStream_t s, const gkob200_matrix& A, const V* b, int64_t b_
                                            static_cast<const V*>(A.values), b, b_stride, nrhs, alpha, beta, c,
                                            c_stride, strategy, A.csr_max_block_nnz, A.workspace,
                                            A.workspace_bytes, nrhs == 1 ? fp : nullptr);
+    }
+    case GKOB200_FMT_ELL:
+        if (A.index_type == GKOB200_I32)
+            return ell_spmv_launch<V, int32_t>(s, A.n_rows, A.ell_stride, A.ell_width,
+                                               static_cast<const int32_t*>(A.ell_col_idxs),
+                                               static_cast<const V*>(A.ell_values), b, b_stride, nrhs, alpha, beta, c,
+                                               c_stride, nrhs == 1 ? fp : nullptr);
+        return ell_spmv_launch<V, int64_t>(s, A.n_rows, A.ell_stride, A.ell_width,
+                                           static_cast<const int64_t*>(A.ell_col_idxs),
+                                           static_cast<const V*>(A.ell_values), b, b_stride, nrhs, alpha, beta, c,
+                                           c_stride, nrhs == 1 ? fp : nullptr);
+    case GKOB200_FMT_SELLP:
+        if (A.index_type == GKOB200_I32)
+            return sellp_spmv_launch<V, int32_t>(s, A.n_rows, A.slice_size, A.slice_sets, A.slice_lengths,
+                                                 static_cast<const int32_t*>(A.col_idxs),
+                                                 static_cast<const V*>(A.values), b, b_stride, nrhs, alpha, beta, c,
+                                                 c_stride, nrhs == 1 ? fp : nullptr);
+        return sellp_spmv_launch<V, int64_t>(s, A.n_rows, A.slice_size, A.slice_sets, A.slice_lengths,
+                                             static_cast<const int64_t*>(A.col_idxs), static_cast<const V*>(A.values),
+                                             b, b_stride, nrhs, alpha, beta, c, c_stride, nrhs == 1 ? fp : nullptr);
+    case GKOB200_FMT_COO:
+        // (no skip/dot fusion: extra work after the solver stopped only touches workspace)
+        if (A.index_type == GKOB200_I32)
+            return coo_spmv_launch<V, int32_t>(s, A.n_rows, A.nnz, static_cast<const int32_t*>(A.row_ptrs),
+                                               static_cast<const int32_t*>(A.col_idxs),
+                                               static_cast<const V*>(A.values), b, b_stride, nrhs, alpha, beta, false,
+                                               c, c_stride, A.workspace, A.workspace_bytes);
+        return coo_spmv_launch<V, int64_t>(s, A.n_rows, A.nnz, static_cast<const int64_t*>(A.row_ptrs),
+                                           static_cast<const int64_t*>(A.col_idxs), static_cast<const V*>(A.values), b,
+                                           b_stride, nrhs, alpha, beta, false, c, c_stride, A.workspace,
+                                           A.workspace_bytes);
+    case GKOB200_FMT_HYBRID: {
+        // ELL part apply, then COO part apply2 [ref: core/matrix/hybrid.cpp:133-160]
+        int rc;
+        if (A.index_type == GKOB200_I32) {
+            rc = ell_spmv_launch<V, int32_t>(s, A.n_rows, A.ell_stride, A.ell_width,
+                                             static_cast<const int32_t*>(A.ell_col_idxs),
+                                             static_cast<const V*>(A.ell_values), b, b_stride, nrhs, alpha, beta, c,
+                                             c_stride, nullptr);
+            if (rc) return rc;
+            return coo_spmv_launch<V, int32_t>(s, A.n_rows, A.coo_nnz, static_cast<const int32_t*>(A.coo_row_idxs),
+                                               static_cast<const int32_t*>(A.coo_col_idxs),
+                                               static_cast<const V*>(A.coo_values), b, b_stride, nrhs, alpha, nullptr,
+                                               true, c, c_stride, A.workspace, A.workspace_bytes);
+        }
+        rc = ell_spmv_launch<V, int64_t>(s, A.n_rows, A.ell_stride, A.ell_width,
+                                         static_cast<const int64_t*>(A.ell_col_idxs),
+                                         static_cast<const V*>(A.ell_values), b, b_stride, nrhs, alpha, beta, c,
+                                         c_stride, nullptr);
+        if (rc) return rc;
+        return coo_spmv_launch<V, int64_t>(s, A.n_rows, A.coo_nnz, static_cast<const int64_t*>(A.coo_row_idxs),
+                                           static_cast<const int64_t*>(A.coo_col_idxs),
+                                           static_cast<const V*>(A.coo_values), b, b_stride, nrhs, alpha, nullptr,
+                                           true, c, c_stride, A.workspace, A.workspace_bytes);
     }
     default:
         return GKOB200_EUNSUPPORTED;

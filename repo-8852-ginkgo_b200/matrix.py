@@ -260,3 +260,273 @@ class Csr(_SparseBase):
         v, i = self.values.element_size(), self.row_ptrs.element_size()
         n, m = self.size
         return self.nnz * (v + i) + (n + 1) * i + m * nrhs * v + n * nrhs * v
+
+
+# --------------------------------------------------------------------------- #
+# integer helpers (device kernels; results bit-exact with the reference)
+# --------------------------------------------------------------------------- #
+def _scan_ws(exec_, n):
+    nbytes = lib.gkob200_prefix_sum_workspace_bytes(n)
+    return torch.empty(max(nbytes, 8), dtype=torch.uint8, device=exec_.device), nbytes
+
+
+def prefix_sum(exec_, t):
+    """In-place exclusive scan of a device tensor (int32/int64; uint64 stored as int64)."""
+    ws, nb = _scan_ws(exec_, t.numel())
+    name = {torch.int32: "i32", torch.int64: "i64"}[t.dtype]
+    check(getattr(lib, f"gkob200_prefix_sum_{name}")(current_stream(), ptr(t), t.numel(), ptr(ws), nb), "prefix_sum")
+    return t
+
+
+def row_nnz_kth_smallest(exec_, row_ptrs, k):
+    """k-th smallest row length (0-based) — what the reference obtains by std::sort of
+    row_nnz on the host (hybrid.hpp:255-270) — from device histograms, no sort."""
+    n = row_ptrs.numel() - 1
+    I = iname(row_ptrs.dtype)
+    mx = torch.zeros(1, dtype=torch.int64, device=exec_.device)
+    check(getattr(lib, f"gkob200_compute_max_row_nnz_{I}")(current_stream(), ptr(row_ptrs), n, ptr(mx)), "max_row_nnz")
+    lo, hi = 0, int(mx.item()) + 1  # answer in [lo, hi)
+    bins = 4096
+    hist = torch.zeros(bins, dtype=torch.int64, device=exec_.device)
+    below = 0  # rows with length < lo
+    while True:
+        width = max(1, -(-(hi - lo) // bins))
+        check(getattr(lib, f"gkob200_row_len_histogram_{I}")(current_stream(), ptr(row_ptrs), n, lo, width, bins,
+                                                              ptr(hist)), "row_len_histogram")
+        h = hist.cpu().numpy()
+        cum = below
+        for b in range(bins):
+            if cum + h[b] > k:
+                if width == 1:
+                    return lo + b
+                lo, hi, below = lo + b * width, lo + (b + 1) * width, cum
+                break
+            cum += h[b]
+        else:
+            raise Error("row_nnz_kth_smallest", -1)
+
+
+class Ell(_SparseBase):
+    """matrix::Ell<V,I>: col_idxs/values[stride * num_stored_elements_per_row], column-major,
+    padding col = -1 / val = 0 (reference include/ginkgo/core/matrix/ell.hpp)."""
+
+    def __init__(self, exec_, size, width, stride, col_idxs, values):
+        self.exec, self.size, self.width, self.stride = exec_, tuple(size), int(width), int(stride)
+        self.col_idxs, self.values = col_idxs, values
+        self.V, self.I = vname(values.dtype), iname(col_idxs.dtype)
+
+    def descriptor(self):
+        d = _abi.Matrix()
+        d.format = _abi.FMT_ELL
+        d.value_type = _abi.F64 if self.V == "f64" else _abi.F32
+        d.index_type = _abi.I32 if self.I == "i32" else _abi.I64
+        d.n_rows, d.n_cols = self.size
+        d.nnz = self.width * self.stride
+        d.ell_stride, d.ell_width = self.stride, self.width
+        d.ell_col_idxs, d.ell_values = self.col_idxs.data_ptr(), self.values.data_ptr()
+        return d
+
+    def kernel(self):
+        return "ell"
+
+    def spmv_bytes(self, nrhs=1):
+        v, i = self.values.element_size(), self.col_idxs.element_size()
+        return self.size[0] * self.width * (v + i) + (self.size[1] + self.size[0]) * nrhs * v
+
+
+class Sellp(_SparseBase):
+    """matrix::Sellp<V,I> (reference include/ginkgo/core/matrix/sellp.hpp): slice_size 64,
+    stride_factor 1 by default; slice_sets/slice_lengths are size_type (uint64, kept in int64
+    tensors)."""
+
+    def __init__(self, exec_, size, slice_size, stride_factor, slice_sets, slice_lengths, col_idxs, values):
+        self.exec, self.size = exec_, tuple(size)
+        self.slice_size, self.stride_factor = int(slice_size), int(stride_factor)
+        self.slice_sets, self.slice_lengths, self.col_idxs, self.values = slice_sets, slice_lengths, col_idxs, values
+        self.V, self.I = vname(values.dtype), iname(col_idxs.dtype)
+
+    def descriptor(self):
+        d = _abi.Matrix()
+        d.format = _abi.FMT_SELLP
+        d.value_type = _abi.F64 if self.V == "f64" else _abi.F32
+        d.index_type = _abi.I32 if self.I == "i32" else _abi.I64
+        d.n_rows, d.n_cols = self.size
+        d.nnz = self.values.numel()
+        d.col_idxs, d.values = self.col_idxs.data_ptr(), self.values.data_ptr()
+        d.slice_size, d.stride_factor = self.slice_size, self.stride_factor
+        d.n_slices = self.slice_lengths.numel()
+        d.slice_sets, d.slice_lengths = self.slice_sets.data_ptr(), self.slice_lengths.data_ptr()
+        return d
+
+    def kernel(self):
+        return "sellp"
+
+    def spmv_bytes(self, nrhs=1):
+        v, i = self.values.element_size(), self.col_idxs.element_size()
+        return (self.values.numel() * (v + i) + (self.slice_lengths.numel() + 1) * 8
+                + (self.size[1] + self.size[0]) * nrhs * v)
+
+
+class Coo(_SparseBase):
+    """matrix::Coo<V,I>: row-sorted triplets (reference include/ginkgo/core/matrix/coo.hpp)."""
+
+    def __init__(self, exec_, size, row_idxs, col_idxs, values):
+        self.exec, self.size = exec_, tuple(size)
+        self.row_idxs, self.col_idxs, self.values = row_idxs, col_idxs, values
+        self.V, self.I = vname(values.dtype), iname(col_idxs.dtype)
+        nb = lib.gkob200_coo_spmv_workspace_bytes(values.numel(), values.element_size())
+        self._ws = torch.empty(nb, dtype=torch.uint8, device=exec_.device)
+
+    def descriptor(self):
+        d = _abi.Matrix()
+        d.format = _abi.FMT_COO
+        d.value_type = _abi.F64 if self.V == "f64" else _abi.F32
+        d.index_type = _abi.I32 if self.I == "i32" else _abi.I64
+        d.n_rows, d.n_cols = self.size
+        d.nnz = self.values.numel()
+        d.row_ptrs, d.col_idxs, d.values = self.row_idxs.data_ptr(), self.col_idxs.data_ptr(), self.values.data_ptr()
+        d.workspace, d.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
+        return d
+
+    def apply2(self, *args):
+        """x += A b  /  x += alpha A b  (reference Coo::apply2, include/ginkgo/core/matrix/coo.hpp)."""
+        if len(args) == 2:
+            alpha, (b, x) = None, args
+        else:
+            alpha, b, x = args
+        fn = getattr(lib, f"gkob200_coo_spmv2_{self.V}_{self.I}")
+        check(fn(current_stream(), self.size[0], self.size[1], self.values.numel(), ptr(self.row_idxs),
+                 ptr(self.col_idxs), ptr(self.values), ptr(b.t), b.stride, b.size[1],
+                 ptr(alpha.t) if alpha is not None else None, ptr(x.t), x.stride, ptr(self._ws), self._ws.numel()),
+              "coo::spmv2")
+        return x
+
+    def kernel(self):
+        return "coo"
+
+    def spmv_bytes(self, nrhs=1):
+        v, i = self.values.element_size(), self.col_idxs.element_size()
+        return self.values.numel() * (v + 2 * i) + self.size[1] * nrhs * v + 2 * self.size[0] * nrhs * v
+
+
+class Hybrid(_SparseBase):
+    """matrix::Hybrid<V,I> = ELL part + COO part (reference include/ginkgo/core/matrix/hybrid.hpp)."""
+
+    def __init__(self, exec_, size, ell, coo):
+        self.exec, self.size, self.ell, self.coo = exec_, tuple(size), ell, coo
+        self.V, self.I = ell.V, ell.I
+
+    def descriptor(self):
+        d = self.ell.descriptor()
+        c = self.coo.descriptor()
+        d.format = _abi.FMT_HYBRID
+        d.coo_nnz = c.nnz
+        d.coo_row_idxs, d.coo_col_idxs, d.coo_values = c.row_ptrs, c.col_idxs, c.values
+        d.workspace, d.workspace_bytes = c.workspace, c.workspace_bytes
+        return d
+
+    def kernel(self):
+        return "hybrid"
+
+    def spmv_bytes(self, nrhs=1):
+        return self.ell.spmv_bytes(nrhs) + self.coo.spmv_bytes(nrhs)
+
+
+class HybridStrategy:
+    """Hybrid::strategy_type family (reference hybrid.hpp:112-380): the ELL width is an order
+    statistic of the row lengths; computed here from device histograms (bit-exact)."""
+
+    def __init__(self, kind, num_columns=0, percent=0.8, ratio=0.0001):
+        self.kind, self.num_columns = kind, num_columns
+        self.percent, self.ratio = min(max(percent, 0.0), 1.0), ratio
+
+    @classmethod
+    def column_limit(cls, n=0):
+        return cls("column_limit", num_columns=n)
+
+    @classmethod
+    def imbalance_limit(cls, percent=0.8):
+        return cls("imbalance_limit", percent=percent)
+
+    @classmethod
+    def imbalance_bounded_limit(cls, percent=0.8, ratio=0.0001):
+        return cls("imbalance_bounded_limit", percent=percent, ratio=ratio)
+
+    @classmethod
+    def minimal_storage_limit(cls, value_bytes=8, index_bytes=4):
+        return cls("imbalance_limit", percent=index_bytes / (value_bytes + 2 * index_bytes))
+
+    @classmethod
+    def automatic(cls):
+        return cls("imbalance_bounded_limit", percent=1.0 / 3.0, ratio=0.001)
+
+    def ell_width(self, exec_, row_ptrs):
+        n = row_ptrs.numel() - 1
+        if self.kind == "column_limit":
+            return self.num_columns
+        if n == 0:
+            return 0
+        pos = int(n * self.percent) if self.percent < 1 else n - 1
+        w = row_nnz_kth_smallest(exec_, row_ptrs, pos)
+        if self.kind == "imbalance_bounded_limit":
+            w = min(w, int(n * self.ratio))
+        return w
+
+
+def _csr_convert_to(self, fmt, strategy=None, slice_size=64, stride_factor=1):
+    """Csr::convert_to(Ell|Sellp|Hybrid|Coo) (reference core/matrix/csr.cpp:256-410)."""
+    exec_, (n, m) = self.exec, self.size
+    dev, V, I = exec_.device, self.V, self.I
+    s = current_stream()
+    if fmt == "coo":
+        rows = torch.empty_like(self.col_idxs)
+        check(getattr(lib, f"gkob200_convert_ptrs_to_idxs_{I}")(s, ptr(self.row_ptrs), n, ptr(rows)), "ptrs_to_idxs")
+        return Coo(exec_, self.size, rows, self.col_idxs, self.values)
+    if fmt == "ell":
+        width, stride = self.max_row_nnz, n
+        cols = torch.empty(width * stride, dtype=self.col_idxs.dtype, device=dev)
+        vals = torch.empty(width * stride, dtype=self.values.dtype, device=dev)
+        check(getattr(lib, f"gkob200_csr_convert_to_ell_{V}_{I}")(s, n, ptr(self.row_ptrs), ptr(self.col_idxs),
+                                                                  ptr(self.values), width, stride, ptr(cols),
+                                                                  ptr(vals)), "csr::convert_to_ell")
+        return Ell(exec_, self.size, width, stride, cols, vals)
+    if fmt == "sellp":
+        ns = -(-n // slice_size)
+        sets = torch.zeros(ns + 1, dtype=torch.int64, device=dev)
+        lens = torch.zeros(max(ns, 1), dtype=torch.int64, device=dev)[:ns]
+        ws, nb = _scan_ws(exec_, ns + 1)
+        check(getattr(lib, f"gkob200_sellp_compute_slice_sets_{I}")(s, ptr(self.row_ptrs), n, slice_size,
+                                                                    stride_factor, ptr(sets), ptr(lens), ptr(ws), nb),
+              "sellp::compute_slice_sets")
+        total = int(sets[ns].item()) * slice_size
+        cols = torch.empty(total, dtype=self.col_idxs.dtype, device=dev)
+        vals = torch.empty(total, dtype=self.values.dtype, device=dev)
+        check(getattr(lib, f"gkob200_csr_convert_to_sellp_{V}_{I}")(s, n, ptr(self.row_ptrs), ptr(self.col_idxs),
+                                                                    ptr(self.values), slice_size, ptr(sets),
+                                                                    ptr(cols), ptr(vals)), "csr::convert_to_sellp")
+        return Sellp(exec_, self.size, slice_size, stride_factor, sets, lens, cols, vals)
+    if fmt == "hybrid":
+        strategy = strategy or HybridStrategy.automatic()
+        ell_lim = min(strategy.ell_width(exec_, self.row_ptrs), m)
+        row_nnz = torch.empty(n, dtype=torch.int64, device=dev)
+        check(getattr(lib, f"gkob200_convert_ptrs_to_sizes_{I}")(s, ptr(self.row_ptrs), n, ptr(row_nnz)),
+              "ptrs_to_sizes")
+        coo_ptrs = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        ws, nb = _scan_ws(exec_, n + 1)
+        check(lib.gkob200_hybrid_compute_coo_row_ptrs(s, ptr(row_nnz), n, ell_lim, ptr(coo_ptrs), ptr(ws), nb),
+              "hybrid::compute_coo_row_ptrs")
+        coo_nnz = int(coo_ptrs[n].item())
+        ecols = torch.empty(ell_lim * n, dtype=self.col_idxs.dtype, device=dev)
+        evals = torch.empty(ell_lim * n, dtype=self.values.dtype, device=dev)
+        crows = torch.empty(coo_nnz, dtype=self.col_idxs.dtype, device=dev)
+        ccols = torch.empty(coo_nnz, dtype=self.col_idxs.dtype, device=dev)
+        cvals = torch.empty(coo_nnz, dtype=self.values.dtype, device=dev)
+        check(getattr(lib, f"gkob200_csr_convert_to_hybrid_{V}_{I}")(
+            s, n, ptr(self.row_ptrs), ptr(self.col_idxs), ptr(self.values), ptr(coo_ptrs), n, ell_lim, ptr(ecols),
+            ptr(evals), ptr(crows), ptr(ccols), ptr(cvals)), "csr::convert_to_hybrid")
+        return Hybrid(exec_, self.size, Ell(exec_, self.size, ell_lim, n, ecols, evals),
+                      Coo(exec_, self.size, crows, ccols, cvals))
+    raise Error(f"convert_to({fmt})", -2)
+
+
+Csr.convert_to = _csr_convert_to
