@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--cpu-baseline-iters", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--spmv-reps", type=int, default=50)
-    ap.add_argument("--format", default="csr", choices=["csr", "sellp", "ell"])
+    ap.add_argument("--format", default="csr", choices=["csr", "sellp", "ell", "hybrid", "coo"])
     return ap.parse_args()
 
 
@@ -191,9 +191,12 @@ def main():
     if args.format != "csr":
         Aop = A.convert_to(args.format)
     iters = args.iters_per_step
+    # the preconditioner is generated from the CSR matrix (Jacobi::generate converts its
+    # system matrix to CSR in the reference too, core/preconditioner/jacobi.cpp)
+    jacobi = gko.preconditioner.Jacobi.build().with_max_block_size(1).on(exec_).generate(A)
     solver = (gko.solver.Cg.build()
               .with_criteria(gko.stop.Iteration(iters))
-              .with_preconditioner(gko.preconditioner.Jacobi.build().with_max_block_size(1))
+              .with_generated_preconditioner(jacobi)
               .with_check_every(max(iters, 1))
               .on(exec_).generate(Aop))
     b_host = torch.ones(n, dtype=torch.float64).pin_memory()

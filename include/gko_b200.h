@@ -269,6 +269,84 @@ GKOB200_DECL_JACOBI_SCALAR(f64, double)
 GKOB200_DECL_JACOBI_SCALAR(f32, float)
 
 /* ------------------------------------------------------------------------- *
+ * BiCGSTAB step kernels  [ref: core/solver/bicgstab_kernels.hpp:55-104; oracle
+ * reference/solver/bicgstab_kernels.cpp:53-213; replaced
+ * common/unified/solver/bicgstab_kernels.cpp:53-213].  step_2 also writes alpha,
+ * step_3 writes omega (from row 0, like the reference's device kernels).
+ * GMRES kernels  [ref: core/solver/{gmres,common_gmres}_kernels.hpp; oracle
+ * reference/solver/{gmres,common_gmres}_kernels.cpp].  krylov_bases is
+ * (krylov_dim+1)*n x k, hessenberg (krylov_dim+1) x krylov_dim*k (entry (i, iter*k + rhs)),
+ * hessenberg_iter points at column block `iter`; final_iter_nums are size_type (uint64).
+ * ------------------------------------------------------------------------- */
+#define GKOB200_DECL_KRYLOV(V, VT)                                                                                \
+    int gkob200_bicgstab_initialize_##V(void* stream, int64_t n, int64_t k, const VT* b, int64_t b_stride, VT* r,  \
+                                        VT* rr, VT* y, VT* s, VT* t, VT* z, VT* v, VT* p, int64_t stride,          \
+                                        VT* prev_rho, VT* rho, VT* alpha, VT* beta, VT* gamma, VT* omega,          \
+                                        uint8_t* stop_status);                                                    \
+    int gkob200_bicgstab_step_1_##V(void* stream, int64_t n, int64_t k, const VT* r, VT* p, const VT* v,           \
+                                    int64_t stride, const VT* rho, const VT* prev_rho, const VT* alpha,            \
+                                    const VT* omega, const uint8_t* stop_status);                                 \
+    int gkob200_bicgstab_step_2_##V(void* stream, int64_t n, int64_t k, const VT* r, VT* s, const VT* v,           \
+                                    int64_t stride, const VT* rho, VT* alpha, const VT* beta,                      \
+                                    const uint8_t* stop_status);                                                  \
+    int gkob200_bicgstab_step_3_##V(void* stream, int64_t n, int64_t k, VT* x, int64_t x_stride, VT* r,            \
+                                    const VT* s, const VT* t, const VT* y, const VT* z, int64_t stride,            \
+                                    const VT* alpha, const VT* beta, const VT* gamma, VT* omega,                   \
+                                    const uint8_t* stop_status);                                                  \
+    int gkob200_bicgstab_finalize_##V(void* stream, int64_t n, int64_t k, VT* x, int64_t x_stride, const VT* y,    \
+                                      int64_t stride, const VT* alpha, uint8_t* stop_status);                      \
+    int gkob200_gmres_initialize_##V(void* stream, int64_t n, int64_t k, int64_t krylov_dim, const VT* b,          \
+                                     int64_t b_stride, VT* residual, int64_t r_stride, VT* givens_sin,             \
+                                     VT* givens_cos, uint8_t* stop_status);                                       \
+    int gkob200_gmres_restart_##V(void* stream, int64_t n, int64_t k, const VT* residual, int64_t r_stride,        \
+                                  const VT* residual_norm, VT* residual_norm_collection, VT* krylov_bases,         \
+                                  uint64_t* final_iter_nums);                                                     \
+    int gkob200_gmres_multi_axpy_##V(void* stream, int64_t n, int64_t k, const VT* krylov_bases, const VT* y,      \
+                                     VT* before_preconditioner, int64_t bp_stride,                                \
+                                     const uint64_t* final_iter_nums, uint8_t* stop_status);                      \
+    int gkob200_gmres_hessenberg_qr_##V(void* stream, int64_t k, VT* givens_sin, VT* givens_cos,                   \
+                                        VT* residual_norm, VT* residual_norm_collection, VT* hessenberg_iter,      \
+                                        int64_t hessenberg_stride, int64_t iter, uint64_t* final_iter_nums,        \
+                                        const uint8_t* stop_status);                                              \
+    int gkob200_gmres_solve_krylov_##V(void* stream, int64_t k, const VT* residual_norm_collection,                \
+                                       const VT* hessenberg, int64_t hessenberg_stride, VT* y,                     \
+                                       const uint64_t* final_iter_nums, const uint8_t* stop_status);
+GKOB200_DECL_KRYLOV(f64, double)
+GKOB200_DECL_KRYLOV(f32, float)
+
+/* ------------------------------------------------------------------------- *
+ * Block-Jacobi  [ref: core/preconditioner/jacobi_kernels.hpp:50-105; oracle
+ * reference/preconditioner/jacobi_kernels.cpp:66-148 (find_blocks), :157-438 (generate:
+ * Gauss-Jordan inversion with max-abs column pivoting), :447-562 (apply); replaced
+ * cuda/preconditioner/jacobi_*.cu].  Storage = Ginkgo's block_interleaved_storage_scheme
+ * (include/ginkgo/core/preconditioner/jacobi.hpp:62-165): block b starts at
+ * group_offset*(b >> group_power) + block_offset*(b & (2^group_power - 1)), entry (r,c) at
+ * r + c*stride with stride = block_offset << group_power.  No adaptive precision.
+ * find_blocks: num_blocks (device, 1 int64) and block_pointers (int32[n+1] capacity).
+ * generate: a zero pivot stops the elimination of that block where it is, exactly like the
+ * reference executor (invert_block's status is ignored, jacobi_kernels.cpp:375-377).
+ * ------------------------------------------------------------------------- */
+size_t gkob200_jacobi_find_blocks_workspace_bytes(int64_t n_rows);
+int gkob200_jacobi_find_blocks_i32(void* stream, int64_t n_rows, const int32_t* row_ptrs, const int32_t* col_idxs,
+                                   int32_t max_block_size, int64_t* num_blocks, int32_t* block_pointers,
+                                   void* workspace, size_t workspace_bytes);
+#define GKOB200_DECL_JACOBI_BLOCK(V, VT)                                                                          \
+    int gkob200_jacobi_block_generate_##V(void* stream, int64_t n_rows, const int32_t* row_ptrs,                   \
+                                          const int32_t* col_idxs, const VT* values, int64_t num_blocks,           \
+                                          const int32_t* block_pointers, int64_t block_offset,                     \
+                                          int64_t group_offset, int group_power, VT* blocks);                      \
+    int gkob200_jacobi_block_simple_apply_##V(void* stream, int64_t num_blocks, const int32_t* block_pointers,     \
+                                              const VT* blocks, int64_t block_offset, int64_t group_offset,        \
+                                              int group_power, int64_t n, int64_t k, const VT* b, int64_t b_stride, \
+                                              VT* x, int64_t x_stride);                                            \
+    int gkob200_jacobi_block_apply_##V(void* stream, int64_t num_blocks, const int32_t* block_pointers,            \
+                                       const VT* blocks, int64_t block_offset, int64_t group_offset,               \
+                                       int group_power, int64_t n, int64_t k, const VT* alpha, const VT* b,        \
+                                       int64_t b_stride, const VT* beta, VT* x, int64_t x_stride);
+GKOB200_DECL_JACOBI_BLOCK(f64, double)
+GKOB200_DECL_JACOBI_BLOCK(f32, float)
+
+/* ------------------------------------------------------------------------- *
  * Synthetic matrix generators (HOST functions writing HOST buffers): the BASELINE
  * shapes, rows [row_begin,row_end) of the global matrix.  kind 0: 2D 5-pt (diag 4),
  * 1: 3D 7-pt (diag 6), 2: 3D 27-pt (diag 26); off-diagonals -1, Dirichlet truncation.

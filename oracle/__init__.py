@@ -296,3 +296,103 @@ def ref_convert(rp, ci, va, n_cols, fmt, hyb_kind="automatic", hyb_param=0, perc
                     ell_vals=ov[:total].copy(), coo_rows=cr[:cn].copy(), coo_cols=cc[:cn].copy(),
                     coo_vals=cv[:cn].copy())
     raise ValueError(fmt)
+
+
+# ---- block-Jacobi, BiCGSTAB, GMRES -------------------------------------------
+def jacobi_storage_scheme(max_block_size, max_block_stride=32):
+    """compute_storage_scheme (include/ginkgo/core/preconditioner/jacobi.hpp:578-610)."""
+    sup = 1
+    while sup < max_block_size:
+        sup *= 2
+    gs = max_block_stride // sup
+    block_offset = max_block_size
+    return block_offset, max_block_size * gs * block_offset, gs.bit_length() - 1
+
+
+def jacobi_find_blocks(rp, ci, max_block_size):
+    n = len(rp) - 1
+    ptrs = np.zeros(n + 1, dtype=np.int32)
+    fn = lib().oracle_jacobi_find_blocks_i32
+    fn.restype = i64
+    nb = fn(i64(n), P(rp), P(ci), C.c_int32(max_block_size), P(ptrs))
+    return int(nb), ptrs[: nb + 1].copy()
+
+
+def jacobi_block_generate(rp, ci, va, max_block_size):
+    """Returns dict(num_blocks, block_ptrs, blocks, block_offset, group_offset, group_power)."""
+    nb, ptrs = jacobi_find_blocks(rp, ci, max_block_size)
+    bo, go, gp = jacobi_storage_scheme(max_block_size)
+    storage = -(-nb // (1 << gp)) * go
+    blocks = np.zeros(storage, dtype=va.dtype)
+    getattr(lib(), f"oracle_jacobi_block_generate_{_v(va.dtype)}")(P(rp), P(ci), P(va), i64(nb), P(ptrs), i64(bo), i64(go),
+                                                                   int(gp), P(blocks))
+    return dict(num_blocks=nb, block_ptrs=ptrs, blocks=blocks, block_offset=bo, group_offset=go, group_power=gp)
+
+
+def jacobi_block_apply(J, b, alpha=None, beta=None, x=None):
+    b2, k = _b2(b)
+    out = np.zeros_like(b2) if x is None else np.ascontiguousarray(x.reshape(len(b2), -1)).copy()
+    dt = b2.dtype
+    getattr(lib(), f"oracle_jacobi_block_apply_{_v(dt)}")(
+        i64(J["num_blocks"]), P(J["block_ptrs"]), P(J["blocks"]), i64(J["block_offset"]), i64(J["group_offset"]),
+        int(J["group_power"]), i64(k), int(alpha is not None), _c(dt, alpha or 0), P(b2), i64(k), _c(dt, beta or 0),
+        P(out), i64(k))
+    return out
+
+
+def _precond_struct(dtype, precond, inv_diag, J):
+    VT = f64 if np.dtype(dtype) == np.float64 else f32
+
+    class Precond(C.Structure):
+        _fields_ = [("kind", C.c_int), ("inv_diag", vp), ("num_blocks", i64), ("bptrs", vp), ("blocks", vp),
+                    ("block_offset", i64), ("group_offset", i64), ("group_power", C.c_int)]
+    p = Precond()
+    p.kind = precond
+    if precond == 1:
+        p.inv_diag = inv_diag.ctypes.data
+    elif precond == 2:
+        p.num_blocks, p.bptrs, p.blocks = J["num_blocks"], J["block_ptrs"].ctypes.data, J["blocks"].ctypes.data
+        p.block_offset, p.group_offset, p.group_power = J["block_offset"], J["group_offset"], J["group_power"]
+    return p
+
+
+def krylov_solve(solver, rp, ci, va, b, x0, precond=0, inv_diag=None, J=None, max_iters=1000, factor=1e-8,
+                 baseline=0, krylov_dim=30):
+    """solver in {"bicgstab", "gmres"}; precond 0 none / 1 scalar Jacobi (inv_diag) / 2 block Jacobi (J from
+    jacobi_block_generate).  Returns (x, iterations, residual_history, stop_status)."""
+    n = len(rp) - 1
+    b2 = np.ascontiguousarray(b.reshape(n, -1))
+    k = b2.shape[1]
+    x = np.ascontiguousarray(x0.reshape(n, -1)).copy()
+    V = _v(va.dtype)
+    hist = np.zeros(max_iters + 2, dtype=va.dtype)
+    stop = np.zeros(k, dtype=np.uint8)
+    p = _precond_struct(va.dtype, precond, inv_diag, J)
+    if solver == "bicgstab":
+        fn = getattr(lib(), f"oracle_bicgstab_solve_csr_i32_{V}")
+        fn.restype = i64
+        it = fn(i64(n), P(rp), P(ci), P(va), C.byref(p), i64(max_iters), _c(va.dtype, factor), int(baseline), i64(k),
+                P(b2), P(x), P(hist), i64(len(hist)), P(stop))
+    else:
+        fn = getattr(lib(), f"oracle_gmres_solve_csr_i32_{V}")
+        fn.restype = i64
+        it = fn(i64(n), P(rp), P(ci), P(va), C.byref(p), i64(max_iters), _c(va.dtype, factor), int(baseline),
+                i64(krylov_dim), i64(k), P(b2), P(x), P(hist), i64(len(hist)), P(stop))
+    return x.reshape(x0.shape), int(it), hist[: it + 1].astype(np.float64), stop
+
+
+def ref_jacobi_generate(rp, ci, va, max_block_size):
+    r = ref()
+    n = len(rp) - 1
+    cap = (n + 64) * 32 * 2 + 4096
+    meta = np.zeros(4, dtype=np.int64)
+    ptrs = np.zeros(n + 2, dtype=np.int32)
+    blocks = np.zeros(cap, dtype=va.dtype)
+    fn = getattr(r, f"ref_jacobi_generate_{_v(va.dtype)}_i32")
+    fn.restype = i64
+    stored = fn(i64(n), i64(len(ci)), P(rp), P(ci), P(va), int(max_block_size), P(meta), P(ptrs), P(blocks), i64(cap))
+    if stored < 0:
+        raise RuntimeError(f"ref_jacobi_generate rc={stored}")
+    nb = int(meta[0])
+    return dict(num_blocks=nb, block_ptrs=ptrs[: nb + 1].copy(), blocks=blocks[:stored].copy(),
+                block_offset=int(meta[1]), group_offset=int(meta[2]), group_power=int(meta[3]))

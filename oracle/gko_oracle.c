@@ -24,7 +24,9 @@
 #undef ORACLE_INDEX_UNSIGNED
 #define IT int32_t
 #define ISFX(name) name##_i32
+#define ORACLE_INDEX_I32
 #include "oracle_index.inc"
+#undef ORACLE_INDEX_I32
 #undef IT
 #undef ISFX
 #define IT int64_t

@@ -53,10 +53,13 @@ struct HistoryLogger : gko::log::Logger {
     mutable std::vector<double> hist;
     mutable int64_t iters = 0;
     void on_iteration_complete(const gko::LinOp*, const gko::size_type& it, const gko::LinOp* r, const gko::LinOp*,
-                               const gko::LinOp*) const override
+                               const gko::LinOp* tau) const override
     {
         iters = static_cast<int64_t>(it);
-        if (auto d = dynamic_cast<const gko::matrix::Dense<V>*>(r)) {
+        if (auto t = dynamic_cast<const gko::matrix::Dense<V>*>(tau)) {
+            // GMRES hands the criterion its implicit residual norm (core/solver/gmres.cpp:236-243)
+            hist.push_back(static_cast<double>(t->get_executor()->copy_val_to_host(t->get_const_values())));
+        } else if (auto d = dynamic_cast<const gko::matrix::Dense<V>*>(r)) {
             auto nrm = gko::matrix::Dense<V>::create(d->get_executor(), gko::dim<2>(1, d->get_size()[1]));
             d->compute_norm2(nrm.get());
             auto h = nrm->get_executor()->get_master();
@@ -292,6 +295,37 @@ int64_t convert_impl(int format, int hyb_kind, int64_t hyb_param, double percent
     }
 }
 
+// ---- block-Jacobi generate through the real reference executor -------------------
+template <typename V, typename I>
+int64_t jacobi_impl(int64_t n, int64_t nnz, const I* rp, const I* ci, const V* va, int max_block_size, int64_t* meta,
+                    I* block_ptrs, V* blocks, int64_t cap)
+{
+    try {
+        auto exec = gko::ReferenceExecutor::create();
+        auto csr = gko::share(csr_view<V, I>(exec, n, n, nnz, rp, ci, va));
+        auto jac = gko::preconditioner::Jacobi<V, I>::build()
+                       .with_max_block_size(static_cast<gko::uint32>(max_block_size))
+                       .on(exec)
+                       ->generate(gko::as<gko::LinOp>(csr));
+        const int64_t nb = jac->get_num_blocks();
+        const auto& sch = jac->get_storage_scheme();
+        meta[0] = nb;
+        meta[1] = sch.block_offset;
+        meta[2] = sch.group_offset;
+        meta[3] = sch.group_power;
+        const int64_t stored = jac->get_num_stored_elements();
+        if (stored > cap) return -3;
+        if (max_block_size > 1) {
+            std::copy_n(jac->get_parameters().block_pointers.get_const_data(), nb + 1, block_ptrs);
+        }
+        std::copy_n(jac->get_blocks(), stored, blocks);
+        return stored;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "ref_wrap: %s\n", e.what());
+        return -1;
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -329,6 +363,17 @@ void ref_set_num_threads(int n) { omp_set_num_threads(n); }
                                     n_rows, n_cols, nnz, rp, ci, va, meta, out_idx_a, out_idx_b, out_vals,       \
                                     out_u64_a, out_u64_b, coo_rows, coo_cols, coo_vals, cap);                    \
     }
+int64_t ref_jacobi_generate_f64_i32(int64_t n, int64_t nnz, const int32_t* rp, const int32_t* ci, const double* va,
+                                    int max_block_size, int64_t* meta, int32_t* block_ptrs, double* blocks,
+                                    int64_t cap)
+{
+    return jacobi_impl<double, int32_t>(n, nnz, rp, ci, va, max_block_size, meta, block_ptrs, blocks, cap);
+}
+int64_t ref_jacobi_generate_f32_i32(int64_t n, int64_t nnz, const int32_t* rp, const int32_t* ci, const float* va,
+                                    int max_block_size, int64_t* meta, int32_t* block_ptrs, float* blocks, int64_t cap)
+{
+    return jacobi_impl<float, int32_t>(n, nnz, rp, ci, va, max_block_size, meta, block_ptrs, blocks, cap);
+}
 REF_CONVERT(f64, double, i32, int32_t)
 REF_CONVERT(f32, float, i32, int32_t)
 REF_CONVERT(f64, double, i64, int64_t)

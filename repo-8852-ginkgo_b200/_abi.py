@@ -112,6 +112,23 @@ def declare(lib):
         d(f"gkob200_compute_max_row_nnz_{I}", [vp, vp, i64, vp])
         d(f"gkob200_sellp_compute_slice_sets_{I}", [vp, vp, i64, i64, i64, vp, vp, vp, sz])
         d(f"gkob200_row_len_histogram_{I}", [vp, vp, i64, u64, u64, C.c_int, vp])
+    # Krylov step kernels
+    for V, T in VT.items():
+        d(f"gkob200_bicgstab_initialize_{V}", [vp, i64, i64, vp, i64] + [vp] * 8 + [i64] + [vp] * 7)
+        d(f"gkob200_bicgstab_step_1_{V}", [vp, i64, i64, vp, vp, vp, i64, vp, vp, vp, vp, vp])
+        d(f"gkob200_bicgstab_step_2_{V}", [vp, i64, i64, vp, vp, vp, i64, vp, vp, vp, vp])
+        d(f"gkob200_bicgstab_step_3_{V}", [vp, i64, i64, vp, i64, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp])
+        d(f"gkob200_bicgstab_finalize_{V}", [vp, i64, i64, vp, i64, vp, i64, vp, vp])
+        d(f"gkob200_gmres_initialize_{V}", [vp, i64, i64, i64, vp, i64, vp, i64, vp, vp, vp])
+        d(f"gkob200_gmres_restart_{V}", [vp, i64, i64, vp, i64, vp, vp, vp, vp])
+        d(f"gkob200_gmres_multi_axpy_{V}", [vp, i64, i64, vp, vp, vp, i64, vp, vp])
+        d(f"gkob200_gmres_hessenberg_qr_{V}", [vp, i64, vp, vp, vp, vp, vp, i64, i64, vp, vp])
+        d(f"gkob200_gmres_solve_krylov_{V}", [vp, i64, vp, vp, i64, vp, vp, vp])
+        d(f"gkob200_jacobi_block_generate_{V}", [vp, i64, vp, vp, vp, i64, vp, i64, i64, C.c_int, vp])
+        d(f"gkob200_jacobi_block_simple_apply_{V}", [vp, i64, vp, vp, i64, i64, C.c_int, i64, i64, vp, i64, vp, i64])
+        d(f"gkob200_jacobi_block_apply_{V}", [vp, i64, vp, vp, i64, i64, C.c_int, i64, i64, vp, vp, i64, vp, vp, i64])
+    d("gkob200_jacobi_find_blocks_workspace_bytes", [i64], sz)
+    d("gkob200_jacobi_find_blocks_i32", [vp, i64, vp, vp, i32, vp, vp, vp, sz])
     # generators (host)
     d("gkob200_gen_stencil_nnz", [C.c_int, i64, i64, i64, i64, i64], i64)
     for V in VT:

@@ -147,13 +147,18 @@ int gkob200_matrix_apply(void* stream, const gkob200_matrix* A, const void* b, i
 int gkob200_solver_create(int kind, const gkob200_matrix* A, const gkob200_precond* M, const gkob200_stop* stop,
                           int64_t nrhs, int64_t krylov_dim, gkob200_solver** out)
 {
-    (void)krylov_dim;
     if (!A || !stop || !out || nrhs < 1) return GKOB200_EINVAL;
     *out = nullptr;
     int rc = GKOB200_EUNSUPPORTED;
     gkob200_solver* s = nullptr;
     if (kind == GKOB200_SOLVER_CG) {
         s = A->value_type == GKOB200_F64 ? make_cg_f64(A, M, stop, nrhs, &rc) : make_cg_f32(A, M, stop, nrhs, &rc);
+    }
+    else if (kind == GKOB200_SOLVER_BICGSTAB) {
+        s = A->value_type == GKOB200_F64 ? make_bicgstab_f64(A, M, stop, nrhs, &rc) : make_bicgstab_f32(A, M, stop, nrhs, &rc);
+    } else if (kind == GKOB200_SOLVER_GMRES) {
+        s = A->value_type == GKOB200_F64 ? make_gmres_f64(A, M, stop, nrhs, krylov_dim, &rc)
+                                         : make_gmres_f32(A, M, stop, nrhs, krylov_dim, &rc);
     }
     if (!s) return rc ? rc : GKOB200_EUNSUPPORTED;
     *out = s;

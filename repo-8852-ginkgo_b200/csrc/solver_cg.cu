@@ -453,9 +453,15 @@ int CgSolver<V>::baseline_norm(cudaStream_t s, const V* b, int64_t bs)
 }
 
 template <typename V>
-int CgSolver<V>::precond_apply(cudaStream_t, const V*, V*)
+int CgSolver<V>::precond_apply(cudaStream_t s, const V* in, V* out)
 {
-    return GKOB200_EUNSUPPORTED;  // block-Jacobi is wired in jacobi_block.cu (see make_cg)
+    ++launch_count;
+    if (M.kind == GKOB200_PRECOND_JACOBI_BLOCK)
+        return typed::jacobi_block_simple_apply(static_cast<V*>(nullptr), s, M.num_blocks,
+                                                static_cast<const int32_t*>(M.block_pointers),
+                                                static_cast<const V*>(M.blocks), M.block_offset, M.group_offset,
+                                                static_cast<int>(M.group_power), n, k, in, k, out, k);
+    return GKOB200_EUNSUPPORTED;
 }
 
 inline int cg_step_1_dispatch(cudaStream_t s, int64_t n, int64_t k, double* p, const double* z, int64_t st,
@@ -530,7 +536,7 @@ int CgSolver<V>::apply_general(cudaStream_t s, const V* b, int64_t bs, V* x, int
         else if (M.kind == GKOB200_PRECOND_JACOBI_SCALAR)
             rc = jac_dispatch(s, n, k, static_cast<const V*>(M.inv_diag), r(), k, z(), k);
         else
-            rc = GKOB200_EUNSUPPORTED;
+            rc = precond_apply(s, r(), z());
         if (rc) return rc;
         if ((rc = dot_dispatch(s, n, k, r(), k, z(), k, sc(S_RHO), ws.p))) return rc;
         if ((rc = norm2_dispatch(s, n, k, r(), k, sc(S_TAU), ws.p))) return rc;

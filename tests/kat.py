@@ -66,3 +66,20 @@ def rel_frobenius(a, b):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     nb = np.linalg.norm(b)
     return np.linalg.norm(a - b) / (nb if nb > 0 else 1.0)
+
+# ---- block-Jacobi KATs: reference/test/preconditioner/jacobi_kernels.cpp ----------------
+# (row_ptrs, col_idxs, max_block_size, expected block pointers)
+JACOBI_FIND_BLOCKS_KATS = [
+    ("FindsNaturalBlocks:160-187", [0, 2, 4, 6, 8], [0, 1, 0, 1, 0, 2, 0, 2], 3, [0, 2, 4]),
+    ("ExecutesSupervariableAgglomeration:190-219", [0, 2, 4, 6, 8, 9], [0, 1, 0, 1, 2, 3, 2, 3, 4], 3, [0, 2, 5]),
+    ("AdheresToBlockSizeBound:222-254", [0, 1, 2, 3, 4, 5, 6, 7], [0, 1, 2, 3, 4, 5, 6], 3, [0, 3, 6, 7]),
+    # fixture matrix (:92-104) with unknown block sizes (:257-272)
+    ("CanBeGeneratedWithUnknownBlockSizes:257-272", [0, 3, 5, 7, 10, 13], [0, 1, 4, 0, 1, 2, 3, 2, 3, 4, 0, 3, 4], 3,
+     [0, 3, 5]),
+]
+# fixture matrix of the suite (:92-104) and InvertsDiagonalBlocks (:275-299) with block pointers {0,2,5}
+JACOBI_MTX = dict(row_ptrs=[0, 3, 5, 7, 10, 13], col_idxs=[0, 1, 4, 0, 1, 2, 3, 2, 3, 4, 0, 3, 4],
+                  values=[4.0, -2.0, -2.0, -1.0, 4.0, 4.0, -2.0, -1.0, 4.0, -2.0, -1.0, -1.0, 4.0])
+JACOBI_BLOCK_PTRS = [0, 2, 5]
+JACOBI_INV_B1 = [[4.0 / 14, 2.0 / 14], [1.0 / 14, 4.0 / 14]]
+JACOBI_INV_B2 = [[14.0 / 48, 8.0 / 48, 4.0 / 48], [4.0 / 48, 16.0 / 48, 8.0 / 48], [1.0 / 48, 4.0 / 48, 14.0 / 48]]

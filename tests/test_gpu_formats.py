@@ -177,14 +177,21 @@ def test_stencil_formats_agree_and_cg_on_sellp(gko, exec_, ora):
     x = np.random.default_rng(6).standard_normal((n, 1))
     want = ora.csr_spmv(rp, ci, va, x)
     dx = gko.matrix.Dense.from_numpy(exec_, x)
-    for fmt in ("ell", "sellp", "hybrid"):
+    for fmt in ("ell", "sellp"):
         M = A.convert_to(fmt)
         dy = gko.matrix.Dense.create(exec_, (n, 1))
         M.apply(dx, dy)
         assert np.array_equal(dy.to_numpy(), want), fmt
-    # automatic hybrid on a stencil: ELL width 27, empty COO
+    # automatic hybrid = min(sorted_len[n/3], n/1000): here 9 -> the other 18 columns go to COO
     H = A.convert_to("hybrid")
-    assert H.ell.width == 27 and H.coo.values.numel() == 0
+    assert H.ell.width == ora.hybrid_ell_width(rp, n, "automatic") == 9
+    dy = gko.matrix.Dense.create(exec_, (n, 1))
+    H.apply(dx, dy)
+    assert (np.abs(dy.to_numpy() - want) / entry_bound(rp, ci, va, x)).max() <= 1e-12
+    # from 30^3 rows on, automatic hybrid on a 27-pt stencil is pure ELL
+    rp2, ci2, va2, n2 = gko.gen.stencil_csr("27pt", 30, 30, 30)
+    H2 = gko.matrix.Csr.from_arrays(exec_, (n2, n2), rp2, ci2, va2).convert_to("hybrid")
+    assert H2.ell.width == 27 and H2.coo.values.numel() == 0
     # CG + scalar Jacobi with the SELL-P operator: fused-dot path of the strided kernel
     S = A.convert_to("sellp")
     M = gko.preconditioner.Jacobi.build().with_max_block_size(1).on(exec_).generate(A)

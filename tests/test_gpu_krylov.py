@@ -1,0 +1,162 @@
+"""Block-Jacobi, BiCGSTAB and GMRES on the GPU vs the oracle (which is pinned bit for bit
+against the compiled reference in tests/test_oracle_krylov.py)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+import kat
+from test_oracle_krylov import block_matrix, jacobi_defined_mask, DENSE3
+
+pytestmark = pytest.mark.gpu
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+def gpu_jacobi(gko, exec_, rp, ci, va, max_bs):
+    A = gko.matrix.Csr.from_arrays(exec_, (len(rp) - 1,) * 2, rp, ci, va)
+    return A, gko.preconditioner.Jacobi.build().with_max_block_size(max_bs).on(exec_).generate(A)
+
+
+@pytest.mark.parametrize("case", kat.JACOBI_FIND_BLOCKS_KATS, ids=lambda c: c[0])
+def test_find_blocks_reference_kats(gko, exec_, case):
+    _, rp, ci, max_bs, expect = case
+    rp, ci = np.array(rp, np.int32), np.array(ci, np.int32)
+    _, J = gpu_jacobi(gko, exec_, rp, ci, np.ones(len(ci)), max_bs)
+    assert J.num_blocks == len(expect) - 1
+    assert list(npy(J.block_pointers)[: J.num_blocks + 1]) == expect
+
+
+@pytest.mark.parametrize("max_bs", [2, 3, 4, 8, 13, 16, 32])
+@pytest.mark.parametrize("n,seed", [(257, 42), (5000, 3), (1, 0)])
+def test_block_jacobi_generate_bit_exact(gko, exec_, ora, max_bs, n, seed):
+    rp, ci, va = block_matrix(n, seed)
+    _, J = gpu_jacobi(gko, exec_, rp, ci, va, max_bs)
+    R = ora.jacobi_block_generate(rp, ci, va, max_bs)
+    assert J.num_blocks == R["num_blocks"]
+    assert np.array_equal(npy(J.block_pointers)[: J.num_blocks + 1], R["block_ptrs"])   # index work: bit-exact
+    assert (J.block_offset, J.group_offset, J.group_power) == (R["block_offset"], R["group_offset"], R["group_power"])
+    d = jacobi_defined_mask(R)
+    assert np.array_equal(npy(J.blocks)[d], R["blocks"][d])                             # same pivots, same rounding
+
+
+def test_find_blocks_long_runs_and_dense_rows(gko, exec_, ora):
+    # long runs of identical rows (cap applies inside a run) next to singletons
+    n = 3000
+    rows = []
+    rng = np.random.default_rng(5)
+    i = 0
+    while i < n:
+        run = int(rng.choice([1, 1, 2, 5, 40, 97]))
+        run = min(run, n - i)
+        pat = sorted(set([i] + [int(c) for c in rng.choice(n, 2)]))
+        rows += [pat] * run
+        i += run
+    rp = np.zeros(n + 1, np.int32)
+    rp[1:] = np.cumsum([len(r) for r in rows])
+    ci = np.array([c for r in rows for c in r], np.int32)
+    for max_bs in (1 + 1, 7, 32):
+        nb, ptrs = ora.jacobi_find_blocks(rp, ci, max_bs)
+        _, J = gpu_jacobi(gko, exec_, rp, ci, np.ones(len(ci)), max_bs)
+        assert J.num_blocks == nb and np.array_equal(npy(J.block_pointers)[: nb + 1], ptrs)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("max_bs", [3, 16, 32])
+@pytest.mark.parametrize("nrhs", [1, 3])
+def test_block_jacobi_apply_bit_exact(gko, exec_, ora, dtype, max_bs, nrhs):
+    rp, ci, va = block_matrix(700, 11, dtype)
+    _, J = gpu_jacobi(gko, exec_, rp, ci, va, max_bs)
+    R = ora.jacobi_block_generate(rp, ci, va, max_bs)
+    rng = np.random.default_rng(2)
+    b = rng.standard_normal((700, nrhs)).astype(dtype)
+    x0 = rng.standard_normal((700, nrhs)).astype(dtype)
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    db, dx = gko.matrix.Dense.from_numpy(exec_, b), gko.matrix.Dense.from_numpy(exec_, x0)
+    J.apply(db, dx)
+    assert np.array_equal(dx.to_numpy(), ora.jacobi_block_apply(R, b))
+    dx = gko.matrix.Dense.from_numpy(exec_, x0)
+    J.apply(gko.matrix.Dense.scalar(exec_, 0.5, tdt), db, gko.matrix.Dense.scalar(exec_, -2.0, tdt), dx)
+    assert np.array_equal(dx.to_numpy(), ora.jacobi_block_apply(R, b, 0.5, -2.0, x0))
+
+
+def build(gko, exec_, kind, A, max_iters, factor, precond_block=0, nrhs=1, krylov_dim=30, check_every=8):
+    f = getattr(gko.solver, kind).build().with_criteria(gko.stop.Iteration(max_iters), gko.stop.ResidualNorm(factor))
+    if precond_block:
+        f = f.with_preconditioner(gko.preconditioner.Jacobi.build().with_max_block_size(precond_block))
+    return f.with_krylov_dim(krylov_dim).with_check_every(check_every).on(exec_).generate(A, nrhs=nrhs)
+
+
+@pytest.mark.parametrize("kind", ["Bicgstab", "Gmres"])
+def test_reference_dense_kat(gko, exec_, kind):
+    # SolvesDenseSystem of reference/test/solver/{bicgstab,gmres}_kernels.cpp: x = {-4,-1,4}
+    rp, ci, va, shape = kat.dense_to_csr(DENSE3)
+    A = gko.matrix.Csr.from_arrays(exec_, shape, rp, ci, va, strategy="classical")
+    s = build(gko, exec_, kind, A, 100, kat.rtol(np.float64))
+    b = gko.matrix.Dense.from_numpy(exec_, np.array([[-1.0], [3.0], [1.0]]))
+    x = gko.matrix.Dense.create(exec_, (3, 1))
+    s.apply(b, x)
+    assert kat.rel_frobenius(x.to_numpy(), [[-4.0], [-1.0], [4.0]]) <= kat.rtol(np.float64) * 1e1
+
+
+@pytest.mark.parametrize("kind", ["Bicgstab", "Gmres"])
+@pytest.mark.parametrize("precond_block", [0, 1, 8, 32])
+@pytest.mark.parametrize("nrhs", [1, 2])
+def test_solvers_match_oracle(gko, exec_, ora, kind, precond_block, nrhs):
+    rp, ci, va = block_matrix(2000, 7)
+    n = 2000
+    A = gko.matrix.Csr.from_arrays(exec_, (n, n), rp, ci, va)
+    rng = np.random.default_rng(1)
+    b = rng.standard_normal((n, nrhs))
+    if nrhs == 2:
+        b[:, 1] *= 1e-2
+    pk = 0 if precond_block == 0 else (1 if precond_block == 1 else 2)
+    diag = sp.csr_matrix((va, ci, rp), shape=(n, n)).diagonal()
+    J = ora.jacobi_block_generate(rp, ci, va, precond_block) if pk == 2 else None
+    x_ref, it_ref, hist_ref, stop_ref = ora.krylov_solve(kind.lower(), rp, ci, va, b, np.zeros_like(b), precond=pk,
+                                                         inv_diag=1.0 / diag, J=J, max_iters=300, factor=1e-10,
+                                                         krylov_dim=10)
+    s = build(gko, exec_, kind, A, 300, 1e-10, precond_block, nrhs, krylov_dim=10, check_every=3)
+    db, dx = gko.matrix.Dense.from_numpy(exec_, b), gko.matrix.Dense.create(exec_, (n, nrhs))
+    s.apply(db, dx)
+    assert abs(s.num_iterations - it_ref) <= 2
+    assert list(s.stop_status) == list(stop_ref)
+    m = min(len(s.residual_history), len(hist_ref), 8)
+    assert np.allclose(s.residual_history[:m], hist_ref[:m], rtol=1e-9)
+    assert np.abs(dx.to_numpy() - x_ref).max() <= 1e-8 * np.abs(x_ref).max()
+    r = b - sp.csr_matrix((va, ci, rp), shape=(n, n)) @ dx.to_numpy()
+    assert np.all(np.linalg.norm(r, axis=0) <= 2e-10 * np.linalg.norm(b, axis=0))
+
+
+@pytest.mark.parametrize("kind", ["Bicgstab", "Gmres"])
+def test_iteration_limit_exact(gko, exec_, ora, kind):
+    rp, ci, va, n = gko.gen.stencil_csr("7pt", 12, 11, 10)
+    A = gko.matrix.Csr.from_arrays(exec_, (n, n), rp, ci, va)
+    b = np.random.default_rng(3).standard_normal((n, 1))
+    for max_iters in (0, 1, 5, 13):
+        x_ref, it_ref, hist_ref, stop_ref = ora.krylov_solve(kind.lower(), rp, ci, va, b, np.zeros_like(b),
+                                                             max_iters=max_iters, factor=1e-30, krylov_dim=4)
+        s = build(gko, exec_, kind, A, max_iters, 1e-30, krylov_dim=4, check_every=2)
+        dx = gko.matrix.Dense.create(exec_, (n, 1))
+        s.apply(gko.matrix.Dense.from_numpy(exec_, b), dx)
+        assert s.num_iterations == it_ref == max_iters
+        assert list(s.stop_status) == list(stop_ref)
+        assert np.allclose(dx.to_numpy(), x_ref, rtol=1e-9, atol=1e-12)
+        assert np.allclose(s.residual_history, hist_ref, rtol=1e-9)
+
+
+def test_bicgstab_fp32_hybrid(gko, exec_, ora):
+    # config 5 in miniature: BiCGSTAB fp32 on a Hybrid (column_limit 16) 27-pt stencil
+    rp, ci, va, n = gko.gen.stencil_csr("27pt", 14, 15, 16, value_dtype=np.float32)
+    A = gko.matrix.Csr.from_arrays(exec_, (n, n), rp, ci, va)
+    H = A.convert_to("hybrid", strategy=gko.matrix.HybridStrategy.column_limit(16))
+    assert H.coo.values.numel() > 0
+    b = np.random.default_rng(9).standard_normal((n, 1)).astype(np.float32)
+    x_ref, it_ref, _, _ = ora.krylov_solve("bicgstab", rp, ci, va, b, np.zeros_like(b), max_iters=200, factor=1e-4)
+    s = build(gko, exec_, "Bicgstab", H, 200, 1e-4)
+    dx = gko.matrix.Dense.create(exec_, (n, 1), torch.float32)
+    s.apply(gko.matrix.Dense.from_numpy(exec_, b), dx)
+    assert abs(s.num_iterations - it_ref) <= 2
+    assert np.abs(dx.to_numpy() - x_ref).max() <= 1e-3 * np.abs(x_ref).max()
