@@ -29,7 +29,9 @@ __device__ __forceinline__ void criterion_check(SolverState* st, int64_t k, cons
                                                 V factor, int64_t max_iters, bool set_finalized,
                                                 uint8_t* stop_status, V* hist, bool advance)
 {
-    const int it = st->iter;
+    // st->iter is what the reference's `iter` becomes at its next "++iter"; a check that
+    // does not start a new iteration (BiCGSTAB's mid-iteration check) sees the current one
+    const int it = advance ? st->iter : st->iter - 1;
     if (hist && advance) hist[it] = tau[0];
     bool one_changed = false, all = false;
     // criterion 1: Iteration

@@ -16,7 +16,7 @@ def block_matrix(n, seed, dtype=np.float64):
     while i < n:
         bs = int(rng.integers(1, 7))
         bs = min(bs, n - i)
-        extra = rng.choice(n, size=int(rng.integers(0, 4)), replace=False)
+        extra = rng.choice(n, size=min(n, int(rng.integers(0, 4))), replace=False)
         pattern = sorted(set(range(i, i + bs)) | set(int(e) for e in extra))
         for r in range(i, i + bs):
             for c in pattern:
