@@ -127,6 +127,87 @@ int64_t gkob200_solver_residual_history(const gkob200_solver* s, double* hist_ho
 /* number of kernel launches + memcpy nodes the last apply enqueued (for gpu_launches) */
 int64_t gkob200_solver_launch_count(const gkob200_solver* s);
 
+/* ------------------------------------------------------------------------- *
+ * Row-partitioned distributed matrix over the GPUs of one box (one process per GPU)
+ * [ref: experimental::distributed::{Partition,Matrix,Vector},
+ *  core/distributed/{partition,matrix,vector}.cpp; the reference uses MPI
+ *  (include/ginkgo/core/base/mpi.hpp), here the used subset — all_to_all of sizes,
+ *  all_to_all_v of gather indices, the per-apply halo exchange and the scalar all_reduce —
+ *  runs on NCCL over NVLink].
+ * ------------------------------------------------------------------------- */
+typedef struct gkob200_dist_comm gkob200_dist_comm;
+typedef struct gkob200_dist_matrix gkob200_dist_matrix;
+
+/* 128-byte NCCL unique id; rank 0 creates it and hands it to the others out of band
+ * (torch.distributed broadcast in the Python harness, MPI_Bcast in a Ginkgo shim). */
+int gkob200_nccl_unique_id(void* out128);
+/* blocking; size == 1 needs no id */
+int gkob200_dist_comm_create(const void* id128, int rank, int size, gkob200_dist_comm** out);
+int gkob200_dist_comm_destroy(gkob200_dist_comm* comm);
+int gkob200_dist_comm_rank(const gkob200_dist_comm* comm);
+int gkob200_dist_comm_size(const gkob200_dist_comm* comm);
+/* [ref: mpi::communicator::all_reduce / all_to_all / all_to_all_v,
+ *  call sites core/distributed/vector.cpp:328-440, matrix.cpp:204-221]; device buffers */
+int gkob200_dist_allreduce_sum_f64(gkob200_dist_comm* comm, void* stream, double* buf, int64_t count);
+int gkob200_dist_allreduce_sum_f32(gkob200_dist_comm* comm, void* stream, float* buf, int64_t count);
+int gkob200_dist_alltoall_i64(gkob200_dist_comm* comm, void* stream, const int64_t* send, int64_t* recv, int64_t count);
+int gkob200_dist_alltoallv_i32(gkob200_dist_comm* comm, void* stream, const int32_t* send,
+                               const int64_t* send_sizes_host, const int64_t* send_offsets_host, int32_t* recv,
+                               const int64_t* recv_sizes_host, const int64_t* recv_offsets_host);
+
+/* Partition kernels [ref: core/distributed/partition_kernels.hpp;
+ * reference/distributed/partition_kernels.cpp:42-160] */
+int gkob200_partition_build_ranges_from_global_size_i64(void* stream, int32_t num_parts, int64_t global_size,
+                                                        int64_t* ranges);
+int gkob200_partition_build_from_contiguous_i64(void* stream, int32_t num_parts, const int64_t* ranges,
+                                                int64_t* range_bounds, int32_t* part_ids);
+int gkob200_partition_build_from_mapping_i64(void* stream, int64_t n, const int32_t* mapping, int64_t* range_bounds,
+                                             int32_t* part_ids, int64_t* num_ranges_dev, void* ws, size_t ws_bytes);
+int gkob200_partition_build_starting_indices_i32_i64(void* stream, const int64_t* range_offsets,
+                                                     const int32_t* range_parts, int64_t num_ranges, int32_t num_parts,
+                                                     int32_t* num_empty_parts, int32_t* ranks, int32_t* sizes);
+
+/* distributed_matrix::build_local_nonlocal [ref: core/distributed/matrix_kernels.hpp:51-70;
+ * reference/distributed/matrix_kernels.cpp:49-236].  Input: global-index COO (int64), any
+ * subset of the global matrix (entries of rows owned by other parts are ignored).
+ * Outputs (capacity nnz each unless noted): local COO with local row/col indices; non-local
+ * COO whose columns are renumbered by rank in the list of unique ghost columns sorted by
+ * (owner part, global column); local_gather_idxs / non_local_to_global (one per ghost column);
+ * recv_sizes[num_parts] (device).  counts_host = {n_local, n_non_local, n_ghost_cols}.
+ * Blocking setup call (allocates its temporaries). */
+#define GKOB200_DECL_DIST(V, VT)                                                                                  \
+    int gkob200_dist_build_local_nonlocal_##V(                                                                    \
+        void* stream, int64_t nnz, const int64_t* rows, const int64_t* cols, const VT* vals, int64_t row_num_ranges, \
+        const int64_t* row_range_bounds, const int32_t* row_part_ids, const int32_t* row_range_starts,             \
+        int64_t col_num_ranges, const int64_t* col_range_bounds, const int32_t* col_part_ids,                      \
+        const int32_t* col_range_starts, int64_t global_cols, int32_t num_parts, int32_t local_part,               \
+        int32_t* local_row_idxs, int32_t* local_col_idxs, VT* local_values, int32_t* non_local_row_idxs,           \
+        int32_t* non_local_col_idxs, VT* non_local_values, int32_t* local_gather_idxs, int32_t* recv_sizes,        \
+        int64_t* non_local_to_global, int64_t* counts_host);                                                      \
+    int gkob200_dist_vector_build_local_##V(void* stream, int64_t nnz, const int64_t* rows, const int64_t* cols,   \
+                                            const VT* vals, int64_t num_ranges, const int64_t* range_bounds,       \
+                                            const int32_t* part_ids, const int32_t* range_starts,                  \
+                                            int32_t local_part, VT* local, int64_t local_stride);
+GKOB200_DECL_DIST(f64, double)
+GKOB200_DECL_DIST(f32, float)
+
+/* distributed::Matrix: local block + non-local block + halo plan.  gather_idxs (device): the
+ * local row indices this rank sends, grouped by destination; send/recv sizes per peer (host).
+ * All descriptors and arrays are borrowed. */
+int gkob200_dist_matrix_create(gkob200_dist_comm* comm, const gkob200_matrix* local, const gkob200_matrix* non_local,
+                               const int32_t* gather_idxs, const int64_t* send_sizes_host,
+                               const int64_t* recv_sizes_host, gkob200_dist_matrix** out);
+int gkob200_dist_matrix_destroy(gkob200_dist_matrix* m);
+/* x_local = A b  /  x_local = alpha A b + beta x_local: pack -> NCCL halo exchange on a side
+ * stream overlapped with the local SpMV -> non-local SpMV
+ * [ref: core/distributed/matrix.cpp:307-369] */
+int gkob200_dist_matrix_apply(gkob200_dist_matrix* m, void* stream, const void* b_local, int64_t b_stride,
+                              int64_t nrhs, const void* alpha, const void* beta, void* x_local, int64_t x_stride);
+/* Distributed CG (kind must be GKOB200_SOLVER_CG; preconditioner none / scalar Jacobi on the
+ * local block): the handle is used with gkob200_solver_apply / _num_iterations / ... above. */
+int gkob200_dist_solver_create(int kind, gkob200_dist_matrix* A, const gkob200_precond* M, const gkob200_stop* stop,
+                               int64_t nrhs, gkob200_solver** out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -396,3 +396,174 @@ def ref_jacobi_generate(rp, ci, va, max_block_size):
     nb = int(meta[0])
     return dict(num_blocks=nb, block_ptrs=ptrs[: nb + 1].copy(), blocks=blocks[:stored].copy(),
                 block_offset=int(meta[1]), group_offset=int(meta[2]), group_power=int(meta[3]))
+
+
+# ---- distributed: partitions, build_local_nonlocal, apply ---------------------
+class OPartition(C.Structure):
+    _fields_ = [("num_ranges", i64), ("bounds", vp), ("part_ids", vp), ("starts", vp)]
+
+
+class Partition:
+    """distributed::Partition<int32,int64> restated (core/distributed/partition.cpp:60-140)."""
+
+    def __init__(self, num_parts, bounds, part_ids):
+        self.num_parts = num_parts
+        self.bounds = np.ascontiguousarray(bounds, dtype=np.int64)
+        self.part_ids = np.ascontiguousarray(part_ids, dtype=np.int32)
+        nr = len(self.part_ids)
+        self.starts = np.zeros(nr, dtype=np.int32)
+        self.sizes = np.zeros(num_parts, dtype=np.int32)
+        fn = lib().oracle_partition_build_starting_indices
+        fn.restype = C.c_int32
+        self.num_empty_parts = fn(P(self.bounds), P(self.part_ids), i64(nr), C.c_int32(num_parts), P(self.starts),
+                                  P(self.sizes))
+        self.size = int(self.bounds[-1])
+
+    @classmethod
+    def uniform(cls, num_parts, global_size):
+        ranges = np.zeros(num_parts + 1, dtype=np.int64)
+        lib().oracle_partition_build_ranges_from_global_size(C.c_int32(num_parts), i64(global_size), P(ranges))
+        return cls(num_parts, ranges, np.arange(num_parts, dtype=np.int32))
+
+    @classmethod
+    def from_mapping(cls, mapping, num_parts):
+        mapping = np.ascontiguousarray(mapping, dtype=np.int32)
+        n = len(mapping)
+        bounds, ids = np.zeros(n + 1, dtype=np.int64), np.zeros(max(n, 1), dtype=np.int32)
+        fn = lib().oracle_partition_build_from_mapping
+        fn.restype = i64
+        nr = fn(i64(n), P(mapping), P(bounds), P(ids))
+        return cls(num_parts, bounds[: nr + 1], ids[:nr])
+
+    def struct(self):
+        s = OPartition()
+        s.num_ranges = len(self.part_ids)
+        s.bounds, s.part_ids, s.starts = self.bounds.ctypes.data, self.part_ids.ctypes.data, self.starts.ctypes.data
+        return s
+
+
+def dist_build_local_nonlocal(rows, cols, vals, part, local_part):
+    nnz = len(rows)
+    rows, cols = np.ascontiguousarray(rows, np.int64), np.ascontiguousarray(cols, np.int64)
+    cap = max(nnz, 1)
+    o = dict(lrow=np.zeros(cap, np.int32), lcol=np.zeros(cap, np.int32), lval=np.zeros(cap, vals.dtype),
+             nrow=np.zeros(cap, np.int32), ncol=np.zeros(cap, np.int32), nval=np.zeros(cap, vals.dtype),
+             gather=np.zeros(cap, np.int32), recv_sizes=np.zeros(part.num_parts, np.int32),
+             nl_to_global=np.zeros(cap, np.int64))
+    counts = np.zeros(3, np.int64)
+    ps = part.struct()
+    getattr(lib(), f"oracle_dist_build_local_nonlocal_{_v(vals.dtype)}")(
+        i64(nnz), P(rows), P(cols), P(vals), C.byref(ps), C.byref(ps), C.c_int32(part.num_parts), C.c_int32(local_part),
+        P(o["lrow"]), P(o["lcol"]), P(o["lval"]), P(o["nrow"]), P(o["ncol"]), P(o["nval"]), P(o["gather"]),
+        P(o["recv_sizes"]), P(o["nl_to_global"]), P(counts))
+    nl, nn, ng = (int(c) for c in counts)
+    for k_ in ("lrow", "lcol", "lval"):
+        o[k_] = o[k_][:nl].copy()
+    for k_ in ("nrow", "ncol", "nval"):
+        o[k_] = o[k_][:nn].copy()
+    o["gather"], o["nl_to_global"] = o["gather"][:ng].copy(), o["nl_to_global"][:ng].copy()
+    return o
+
+
+def ref_dist_build(rows, cols, vals, local_part, num_parts, global_size, mapping=None):
+    """The real reference kernels (Partition + build_local_nonlocal); returns (parts dict, partition meta)."""
+    r = ref()
+    nnz = len(rows)
+    cap = max(nnz, 1)
+    o = dict(lrow=np.zeros(cap, np.int32), lcol=np.zeros(cap, np.int32), lval=np.zeros(cap, np.float64),
+             nrow=np.zeros(cap, np.int32), ncol=np.zeros(cap, np.int32), nval=np.zeros(cap, np.float64),
+             gather=np.zeros(cap, np.int32), recv_sizes=np.zeros(num_parts, np.int32),
+             nl_to_global=np.zeros(cap, np.int64))
+    counts = np.zeros(3, np.int64)
+    meta = np.zeros(4 * (global_size + 2) + num_parts + 8, np.int64)
+    mode = 0 if mapping is None else 2
+    mp = None if mapping is None else np.ascontiguousarray(mapping, np.int32)
+    rc = r.ref_dist_build_f64(mode, num_parts, i64(global_size), None, P(mp), i64(nnz),
+                              P(np.ascontiguousarray(rows, np.int64)), P(np.ascontiguousarray(cols, np.int64)),
+                              P(np.ascontiguousarray(vals, np.float64)), int(local_part), P(counts), P(o["lrow"]),
+                              P(o["lcol"]), P(o["lval"]), P(o["nrow"]), P(o["ncol"]), P(o["nval"]), P(o["gather"]),
+                              P(o["recv_sizes"]), P(o["nl_to_global"]), P(meta))
+    if rc != 0:
+        raise RuntimeError(f"ref_dist_build rc={rc}")
+    nl, nn, ng = (int(c) for c in counts)
+    for k_ in ("lrow", "lcol", "lval"):
+        o[k_] = o[k_][:nl].copy()
+    for k_ in ("nrow", "ncol", "nval"):
+        o[k_] = o[k_][:nn].copy()
+    o["gather"], o["nl_to_global"] = o["gather"][:ng].copy(), o["nl_to_global"][:ng].copy()
+    nr = int(meta[0])
+    pm = dict(bounds=meta[1: nr + 2].copy(), part_ids=meta[nr + 2: 2 * nr + 2].astype(np.int32),
+              starts=meta[2 * nr + 2: 3 * nr + 2].astype(np.int32),
+              sizes=meta[3 * nr + 2: 3 * nr + 2 + num_parts].astype(np.int32))
+    return o, pm
+
+
+def coo_to_csr(n_rows, rows, cols, vals):
+    rp = np.zeros(n_rows + 1, dtype=np.int32)
+    lib().oracle_convert_idxs_to_ptrs_i32(P(np.ascontiguousarray(rows, np.int32)), i64(len(rows)), i64(n_rows), P(rp))
+    return rp, np.ascontiguousarray(cols, np.int32), np.ascontiguousarray(vals)
+
+
+def dist_plan(parts_per_rank):
+    """The exchange of distributed::Matrix::read_distributed (core/distributed/matrix.cpp:197-221)
+    for all ranks at once: send_sizes[p][q] = recv_sizes[q][p]; gather_idxs of rank p = the
+    gather lists its receivers q computed, in rank order."""
+    Pn = len(parts_per_rank)
+    recv = np.array([pp["recv_sizes"] for pp in parts_per_rank], dtype=np.int64)
+    send = recv.T.copy()
+    gathers = []
+    for p in range(Pn):
+        chunks = []
+        for q in range(Pn):
+            off = int(recv[q, :p].sum())
+            chunks.append(parts_per_rank[q]["gather"][off: off + int(recv[q, p])])
+        gathers.append(np.concatenate(chunks) if chunks else np.zeros(0, np.int32))
+    return send, recv, gathers
+
+
+def dist_apply(parts_per_rank, part, b_global, alpha=None, beta=None, x_global=None):
+    """distributed::Matrix::apply restated for all ranks in one process
+    (core/distributed/matrix.cpp:263-369): pack with row_gather, exchange, local apply, then
+    x += A_nl * recv.  Returns the global result vector (rows in partition order)."""
+    Pn = len(parts_per_rank)
+    send, recv, gathers = dist_plan(parts_per_rank)
+    b_loc = [global_to_local(part, b_global, p) for p in range(Pn)]
+    send_bufs = [b_loc[p][gathers[p]] for p in range(Pn)]
+    out = np.zeros_like(b_global) if x_global is None else x_global.copy()
+    for p in range(Pn):
+        pp = parts_per_rank[p]
+        n_loc = int(part.sizes[p])
+        ghosts = []
+        for q in range(Pn):  # what q sends to p sits at q's send offset for p
+            off = int(send[q, :p].sum())
+            ghosts.append(send_bufs[q][off: off + int(send[q, p])])
+        ghost = np.concatenate(ghosts) if ghosts else np.zeros((0,) + b_global.shape[1:], b_global.dtype)
+        lrp, lci, lva = coo_to_csr(n_loc, pp["lrow"], pp["lcol"], pp["lval"])
+        nrp, nci, nva = coo_to_csr(n_loc, pp["nrow"], pp["ncol"], pp["nval"])
+        x_loc = global_to_local(part, out, p)
+        if alpha is None:
+            x_loc = csr_spmv(lrp, lci, lva, b_loc[p])
+            if len(ghost):
+                x_loc = csr_spmv(nrp, nci, nva, ghost, 1.0, 1.0, x_loc)
+        else:
+            x_loc = csr_spmv(lrp, lci, lva, b_loc[p], alpha, beta, x_loc)
+            if len(ghost):
+                x_loc = csr_spmv(nrp, nci, nva, ghost, alpha, 1.0, x_loc)
+        local_to_global(part, out, p, x_loc)
+    return out
+
+
+def _local_rows(part, p):
+    idx = []
+    for r in range(len(part.part_ids)):
+        if part.part_ids[r] == p:
+            idx.append(np.arange(part.bounds[r], part.bounds[r + 1]))
+    return np.concatenate(idx) if idx else np.zeros(0, np.int64)
+
+
+def global_to_local(part, v, p):
+    return np.ascontiguousarray(v[_local_rows(part, p)])
+
+
+def local_to_global(part, v, p, loc):
+    v[_local_rows(part, p)] = loc

@@ -109,4 +109,6 @@ void oracle_hybrid_compute_coo_row_ptrs(const uint64_t* row_nnz, int64_t n, uint
 #undef SQRT
 #undef FABS
 
+#include "oracle_dist.inc"
+
 int oracle_version(void) { return 100; }

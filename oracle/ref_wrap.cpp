@@ -5,6 +5,9 @@
 // implementation (`cpu_baseline.kind == "reference"`).  Our code; it only calls
 // Ginkgo's public API.  Never loaded by the product path.
 #include <ginkgo/ginkgo.hpp>
+#include <ginkgo/core/distributed/partition.hpp>
+
+#include "core/distributed/matrix_kernels.hpp"
 
 #include <omp.h>
 
@@ -326,6 +329,67 @@ int64_t jacobi_impl(int64_t n, int64_t nnz, const I* rp, const I* ci, const V* v
     }
 }
 
+// ---- distributed index maps through the real reference kernels (no MPI needed: the
+// reference's own tests loop over local_part in one process,
+// reference/test/distributed/matrix_kernels.cpp:86-152) ------------------------------
+using Part = gko::experimental::distributed::Partition<int32_t, int64_t>;
+
+std::unique_ptr<Part> make_partition(std::shared_ptr<const gko::Executor> exec, int mode, int num_parts,
+                                     int64_t global_size, const int64_t* ranges, const int32_t* mapping)
+{
+    if (mode == 0) return Part::build_from_global_size_uniform(exec, num_parts, global_size);
+    if (mode == 1) return Part::build_from_contiguous(exec, view<int64_t>(exec, num_parts + 1, ranges));
+    return Part::build_from_mapping(exec, view<int32_t>(exec, global_size, mapping), num_parts);
+}
+
+template <typename V>
+int dist_build_impl(int mode, int num_parts, int64_t global_size, const int64_t* ranges, const int32_t* mapping,
+                    int64_t nnz, const int64_t* rows, const int64_t* cols, const V* vals, int local_part,
+                    int64_t* counts, int32_t* lrow, int32_t* lcol, V* lval, int32_t* nrow, int32_t* ncol, V* nval,
+                    int32_t* gather, int32_t* recv_sizes, int64_t* nl_to_global, int64_t* part_meta)
+{
+    try {
+        auto exec = gko::ReferenceExecutor::create();
+        auto part = make_partition(exec, mode, num_parts, global_size, ranges, mapping);
+        gko::device_matrix_data<V, int64_t> input{exec, gko::dim<2>(part->get_size(), part->get_size()),
+                                                  view<int64_t>(exec, nnz, rows), view<int64_t>(exec, nnz, cols),
+                                                  view<V>(exec, nnz, vals)};
+        gko::array<int32_t> a_lrow{exec}, a_lcol{exec}, a_nrow{exec}, a_ncol{exec}, a_gather{exec};
+        gko::array<V> a_lval{exec}, a_nval{exec};
+        gko::array<int32_t> a_recv{exec, static_cast<gko::size_type>(num_parts)};
+        gko::array<int64_t> a_nl2g{exec};
+        gko::kernels::reference::distributed_matrix::build_local_nonlocal(
+            exec, input, part.get(), part.get(), local_part, a_lrow, a_lcol, a_lval, a_nrow, a_ncol, a_nval, a_gather,
+            a_recv, a_nl2g);
+        counts[0] = a_lrow.get_num_elems();
+        counts[1] = a_nrow.get_num_elems();
+        counts[2] = a_gather.get_num_elems();
+        std::copy_n(a_lrow.get_const_data(), counts[0], lrow);
+        std::copy_n(a_lcol.get_const_data(), counts[0], lcol);
+        std::copy_n(a_lval.get_const_data(), counts[0], lval);
+        std::copy_n(a_nrow.get_const_data(), counts[1], nrow);
+        std::copy_n(a_ncol.get_const_data(), counts[1], ncol);
+        std::copy_n(a_nval.get_const_data(), counts[1], nval);
+        std::copy_n(a_gather.get_const_data(), counts[2], gather);
+        std::copy_n(a_nl2g.get_const_data(), counts[2], nl_to_global);
+        std::copy_n(a_recv.get_const_data(), num_parts, recv_sizes);
+        // partition description: num_ranges, then range_bounds[num_ranges+1], part_ids, starting idxs, part sizes
+        if (part_meta) {
+            const int64_t nr = part->get_num_ranges();
+            int64_t* o = part_meta;
+            *o++ = nr;
+            for (int64_t i = 0; i <= nr; ++i) *o++ = part->get_range_bounds()[i];
+            for (int64_t i = 0; i < nr; ++i) *o++ = part->get_part_ids()[i];
+            for (int64_t i = 0; i < nr; ++i) *o++ = part->get_range_starting_indices()[i];
+            for (int i = 0; i < num_parts; ++i) *o++ = part->get_part_sizes()[i];
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "ref_wrap: %s\n", e.what());
+        return -1;
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -363,6 +427,15 @@ void ref_set_num_threads(int n) { omp_set_num_threads(n); }
                                     n_rows, n_cols, nnz, rp, ci, va, meta, out_idx_a, out_idx_b, out_vals,       \
                                     out_u64_a, out_u64_b, coo_rows, coo_cols, coo_vals, cap);                    \
     }
+int ref_dist_build_f64(int mode, int num_parts, int64_t global_size, const int64_t* ranges, const int32_t* mapping,
+                       int64_t nnz, const int64_t* rows, const int64_t* cols, const double* vals, int local_part,
+                       int64_t* counts, int32_t* lrow, int32_t* lcol, double* lval, int32_t* nrow, int32_t* ncol,
+                       double* nval, int32_t* gather, int32_t* recv_sizes, int64_t* nl_to_global, int64_t* part_meta)
+{
+    return dist_build_impl<double>(mode, num_parts, global_size, ranges, mapping, nnz, rows, cols, vals, local_part,
+                                   counts, lrow, lcol, lval, nrow, ncol, nval, gather, recv_sizes, nl_to_global,
+                                   part_meta);
+}
 int64_t ref_jacobi_generate_f64_i32(int64_t n, int64_t nnz, const int32_t* rp, const int32_t* ci, const double* va,
                                     int max_block_size, int64_t* meta, int32_t* block_ptrs, double* blocks,
                                     int64_t cap)

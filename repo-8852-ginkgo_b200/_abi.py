@@ -147,3 +147,25 @@ def declare(lib):
     d("gkob200_solver_stop_status", [vp, vp])
     d("gkob200_solver_residual_history", [vp, vp, i64], i64)
     d("gkob200_solver_launch_count", [vp], i64)
+    # distributed
+    d("gkob200_nccl_unique_id", [vp])
+    d("gkob200_dist_comm_create", [vp, C.c_int, C.c_int, C.POINTER(vp)])
+    d("gkob200_dist_comm_destroy", [vp])
+    d("gkob200_dist_comm_rank", [vp])
+    d("gkob200_dist_comm_size", [vp])
+    d("gkob200_dist_allreduce_sum_f64", [vp, vp, vp, i64])
+    d("gkob200_dist_allreduce_sum_f32", [vp, vp, vp, i64])
+    d("gkob200_dist_alltoall_i64", [vp, vp, vp, vp, i64])
+    d("gkob200_dist_alltoallv_i32", [vp, vp, vp, vp, vp, vp, vp, vp])
+    d("gkob200_partition_build_ranges_from_global_size_i64", [vp, i32, i64, vp])
+    d("gkob200_partition_build_from_contiguous_i64", [vp, i32, vp, vp, vp])
+    d("gkob200_partition_build_from_mapping_i64", [vp, i64, vp, vp, vp, vp, vp, sz])
+    d("gkob200_partition_build_starting_indices_i32_i64", [vp, vp, vp, i64, i32, vp, vp, vp])
+    for V in VT:
+        d(f"gkob200_dist_build_local_nonlocal_{V}",
+          [vp, i64, vp, vp, vp, i64, vp, vp, vp, i64, vp, vp, vp, i64, i32, i32] + [vp] * 10)
+        d(f"gkob200_dist_vector_build_local_{V}", [vp, i64, vp, vp, vp, i64, vp, vp, vp, i32, vp, i64])
+    d("gkob200_dist_matrix_create", [vp, MP, MP, vp, vp, vp, C.POINTER(vp)])
+    d("gkob200_dist_matrix_destroy", [vp])
+    d("gkob200_dist_matrix_apply", [vp, vp, vp, i64, i64, vp, vp, vp, i64])
+    d("gkob200_dist_solver_create", [C.c_int, vp, PP, SP, i64, C.POINTER(vp)])

@@ -1,0 +1,561 @@
+// distributed_matrix.cu — row-partitioned distributed::Matrix apply and distributed CG
+// over the GPUs of one NVLink/NVSwitch box, one process per GPU.
+//
+// Replaces experimental::distributed::Matrix::{communicate, apply_impl}
+// (reference core/distributed/matrix.cpp:263-369) and the all_reduce steps of
+// experimental::distributed::Vector (core/distributed/vector.cpp:317-407).  The reference
+// packs with row_gather, calls exec->synchronize() (a device-wide sync), stages through
+// HOST buffers unless MPI is GPU-aware and posts MPI_Ialltoallv; here
+//   * the pack kernel runs on the compute stream, an event hands the send buffer to a
+//     dedicated communication stream, the halo moves GPU->GPU as grouped ncclSend/ncclRecv
+//     (NVLink 5 through NVSwitch, device buffers only),
+//   * the local SpMV overlaps the exchange on the compute stream,
+//   * a second event gates the non-local SpMV  x += A_nl * ghost,
+//   * dot products are reduced with ncclAllReduce on 1-2 scalars that never visit the host.
+// No device-wide synchronisation anywhere on the path.
+#include <nccl.h>
+
+#include <cstring>
+#include <vector>
+
+#include "solver_common.cuh"
+
+#define GKOB200_NCCL(call)                                        \
+    do {                                                          \
+        ncclResult_t r__ = (call);                                \
+        if (r__ != ncclSuccess) return 1000 + static_cast<int>(r__); \
+    } while (0)
+
+struct gkob200_dist_comm {
+    ncclComm_t comm = nullptr;
+    int rank = 0, size = 1;
+    cudaStream_t comm_stream = nullptr;
+};
+
+struct gkob200_dist_matrix {
+    gkob200_dist_comm* comm = nullptr;
+    gkob200_matrix local{}, non_local{};
+    const int32_t* gather_idxs = nullptr;  // device, send_total entries (local row indices)
+    std::vector<int64_t> send_sizes, send_offsets, recv_sizes, recv_offsets;
+    int64_t send_total = 0, recv_total = 0;
+    gkob200::DevBuf send_buf, recv_buf, consts;
+    int64_t buf_nrhs = 0;
+    cudaEvent_t packed = nullptr, received = nullptr;
+    int64_t launches = 0;
+};
+
+namespace gkob200 {
+namespace {
+
+template <typename V>
+ncclDataType_t nccl_type();
+template <>
+ncclDataType_t nccl_type<double>() { return ncclDouble; }
+template <>
+ncclDataType_t nccl_type<float>() { return ncclFloat; }
+
+template <typename V>
+__global__ void __launch_bounds__(256)
+    pack_halo(int64_t n_send, int64_t k, const int32_t* __restrict__ gather, const V* __restrict__ b, int64_t bs,
+              V* __restrict__ out, const int* skip)
+{
+    if (skip && *skip) return;
+    const int64_t total = n_send * k;
+    for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
+         t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t i = t / k, j = t % k;
+        out[t] = b[static_cast<int64_t>(gather[i]) * bs + j];
+    }
+}
+
+template <typename V>
+int ensure_buffers(gkob200_dist_matrix* m, int64_t nrhs)
+{
+    if (m->buf_nrhs >= nrhs && m->consts.p) return 0;
+    int rc;
+    if ((rc = m->send_buf.alloc(static_cast<size_t>(m->send_total * nrhs + 1) * sizeof(V)))) return rc;
+    if ((rc = m->recv_buf.alloc(static_cast<size_t>(m->recv_total * nrhs + 1) * sizeof(V)))) return rc;
+    if (!m->consts.p) {
+        if ((rc = m->consts.alloc(2 * sizeof(V)))) return rc;
+        const V one = V(1);
+        GKOB200_CUDA(cudaMemcpy(m->consts.p, &one, sizeof(V), cudaMemcpyHostToDevice));
+    }
+    m->buf_nrhs = nrhs;
+    return 0;
+}
+
+// x = A b  or  x = alpha A b + beta x  on the local rows.  `fusion` (nrhs == 1): skip flag
+// and the dot w.(A b) are attached to the LAST SpMV of the sequence.
+template <typename V>
+int dist_apply(gkob200_dist_matrix* m, cudaStream_t s, const V* b, int64_t bs, int64_t nrhs, const V* alpha,
+               const V* beta, V* x, int64_t xs, const SpmvFusion<V>* fusion)
+{
+    int rc;
+    if ((rc = ensure_buffers<V>(m, nrhs))) return rc;
+    gkob200_dist_comm* c = m->comm;
+    const bool has_halo = (m->send_total > 0 || m->recv_total > 0) && c && c->size > 1;
+    V* send = m->send_buf.as<V>();
+    V* recv = m->recv_buf.as<V>();
+    const int* skip = fusion ? fusion->skip : nullptr;
+    if (has_halo) {
+        if (m->send_total > 0) {
+            pack_halo<V><<<grid_for(m->send_total * nrhs, 256, 4), 256, 0, s>>>(m->send_total, nrhs, m->gather_idxs, b, bs,
+                                                                               send, skip);
+            GKOB200_CHECK_LAUNCH();
+            ++m->launches;
+        }
+        GKOB200_CUDA(cudaEventRecord(m->packed, s));
+        GKOB200_CUDA(cudaStreamWaitEvent(c->comm_stream, m->packed, 0));
+        GKOB200_NCCL(ncclGroupStart());
+        for (int p = 0; p < c->size; ++p) {
+            if (p == c->rank) continue;
+            if (m->send_sizes[p] > 0)
+                GKOB200_NCCL(ncclSend(send + m->send_offsets[p] * nrhs, static_cast<size_t>(m->send_sizes[p] * nrhs),
+                                      nccl_type<V>(), p, c->comm, c->comm_stream));
+            if (m->recv_sizes[p] > 0)
+                GKOB200_NCCL(ncclRecv(recv + m->recv_offsets[p] * nrhs, static_cast<size_t>(m->recv_sizes[p] * nrhs),
+                                      nccl_type<V>(), p, c->comm, c->comm_stream));
+        }
+        GKOB200_NCCL(ncclGroupEnd());
+        GKOB200_CUDA(cudaEventRecord(m->received, c->comm_stream));
+        ++m->launches;
+    }
+    const bool nl = has_halo && m->recv_total > 0 && m->non_local.nnz > 0;
+    // local block (overlaps the halo exchange)
+    SpmvFusion<V> fl;
+    if (fusion) {
+        fl = *fusion;
+        if (nl) {  // the dot belongs to the final result: computed by the non-local SpMV
+            fl.w = nullptr;
+            fl.out = nullptr;
+        }
+    }
+    if ((rc = matrix_apply<V>(s, m->local, b, bs, nrhs, alpha, beta, x, xs, fusion ? &fl : nullptr))) return rc;
+    ++m->launches;
+    if (has_halo) GKOB200_CUDA(cudaStreamWaitEvent(s, m->received, 0));
+    if (nl) {
+        // x += alpha * A_nl * ghost   (reference: non_local_mtx_->apply(alpha|one, recv, one, x))
+        const V* one = m->consts.as<V>();
+        if ((rc = matrix_apply<V>(s, m->non_local, recv, nrhs, nrhs, alpha ? alpha : one, one, x, xs, fusion))) return rc;
+        ++m->launches;
+    }
+    return 0;
+}
+
+// ------------------------------- distributed CG --------------------------------
+enum { D_RHO = 0, D_PREV_RHO, D_BETA, D_TAU, D_ORIG_TAU, D_RED0, D_RED1, D_COUNT };
+
+template <typename V>
+struct DistCgParams {
+    int64_t n;
+    V *x, *r, *z, *p, *q;
+    const V* inv_diag;
+    V* sc;
+    SolverState* st;
+    uint8_t* stop_status;
+    V* hist;
+    V factor;
+    int64_t max_iters;
+    void* ws;
+};
+
+// x += t p ; r -= t q ; z = M^-1 r ; partial sums (r.z, r.r) -> sc[D_RED0..1]
+template <typename V, int Mode, bool First>
+__global__ void __launch_bounds__(256) dist_cg_update(DistCgParams<V> P)
+{
+    if (P.st->stopped) return;
+    V t = V(0);
+    bool upd = false;
+    if (!First) {
+        const V beta = P.sc[D_BETA];
+        upd = beta != V(0);
+        if (upd) t = div_rn(P.sc[D_RHO], beta);
+    }
+    V acc[2] = {V(0), V(0)};
+    const int64_t step = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < P.n; i += step) {
+        V ri = P.r[i];
+        if (upd) {
+            P.x[i] = add_rn(P.x[i], mul_rn(t, P.p[i]));
+            ri = sub_rn(ri, mul_rn(t, P.q[i]));
+            P.r[i] = ri;
+        }
+        V zi = ri;
+        if (Mode == 1) {
+            zi = mul_rn(ri, P.inv_diag[i]);
+            P.z[i] = zi;
+        }
+        acc[0] += ri * zi;
+        acc[1] += ri * ri;
+    }
+    V* sc = P.sc;
+    grid_reduce<2>(acc, ws_partials<V>(P.ws), ws_ticket(P.ws), [sc](V(&tot)[2]) {
+        sc[D_RED0] = tot[0];
+        sc[D_RED1] = tot[1];
+    });
+}
+
+// after the all-reduce: rho bookkeeping + criterion on the GLOBAL residual norm
+template <typename V, bool First>
+__global__ void dist_cg_scalars(DistCgParams<V> P)
+{
+    if (P.st->stopped) return;
+    if (!First) P.sc[D_PREV_RHO] = P.sc[D_RHO];
+    P.sc[D_RHO] = P.sc[D_RED0];
+    P.sc[D_TAU] = sqrt_rn(P.sc[D_RED1]);
+    criterion_check(P.st, 1, P.sc + D_TAU, P.sc + D_ORIG_TAU, P.factor, P.max_iters, true, P.stop_status, P.hist, true);
+}
+
+template <typename V, bool ZisR>
+__global__ void __launch_bounds__(256) dist_cg_direction(DistCgParams<V> P)
+{
+    if (P.st->stopped) return;
+    const V prev = P.sc[D_PREV_RHO];
+    const bool zero_prev = prev == V(0);
+    const V t = zero_prev ? V(0) : div_rn(P.sc[D_RHO], prev);
+    const V* __restrict__ z = ZisR ? P.r : P.z;
+    const int64_t step = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < P.n; i += step)
+        P.p[i] = zero_prev ? z[i] : add_rn(z[i], mul_rn(t, P.p[i]));
+}
+
+template <typename V>
+__global__ void __launch_bounds__(256) sq_norm_partial(int64_t n, const V* __restrict__ a, V* out, void* ws)
+{
+    V acc[1] = {V(0)};
+    const int64_t step = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += step) acc[0] += a[i] * a[i];
+    grid_reduce<1>(acc, ws_partials<V>(ws), ws_ticket(ws), [out](V(&tot)[1]) { out[0] = tot[0]; });
+}
+template <typename V>
+__global__ void sqrt_to(V* dst, const V* src) { dst[0] = sqrt_rn(src[0]); }
+template <typename V>
+__global__ void set_one(V* dst) { dst[0] = V(1); }
+
+template <typename V>
+struct DistCgSolver : SolverBase<V> {
+    using B = SolverBase<V>;
+    using B::M; using B::k; using B::n; using B::stop; using B::launch_count;
+    gkob200_dist_matrix* dm = nullptr;
+    DevBuf vecs, scal, bigws;
+    int64_t ws_blocks = 0;
+
+    int init()
+    {
+        this->A = dm->local;  // n_rows == local rows; square check in init_base is on the local block
+        int rc = this->init_base();
+        if (rc) return rc;
+        if (k != 1) return GKOB200_EUNSUPPORTED;
+        // the p.q dot is fused into the last SpMV of the distributed apply
+        if (!matrix_apply_fuses_dot(dm->local, 1) || (dm->non_local.nnz > 0 && !matrix_apply_fuses_dot(dm->non_local, 1)))
+            return GKOB200_EUNSUPPORTED;
+        if (M.kind != GKOB200_PRECOND_NONE && M.kind != GKOB200_PRECOND_JACOBI_SCALAR) return GKOB200_EUNSUPPORTED;
+        if ((rc = vecs.alloc(static_cast<size_t>(n) * 4 * sizeof(V)))) return rc;
+        if ((rc = scal.alloc(D_COUNT * sizeof(V)))) return rc;
+        ws_blocks = ceildiv(n, 128) + 1;
+        if (ws_blocks < kReduceMaxBlocks) ws_blocks = kReduceMaxBlocks;
+        return bigws.alloc(256 + static_cast<size_t>(ws_blocks) * kReduceMaxVals * sizeof(double));
+    }
+
+    DistCgParams<V> params(V* x)
+    {
+        DistCgParams<V> P;
+        P.n = n;
+        P.x = x;
+        P.r = vecs.as<V>();
+        P.z = P.r + n;
+        P.p = P.z + n;
+        P.q = P.p + n;
+        P.inv_diag = M.kind == GKOB200_PRECOND_JACOBI_SCALAR ? static_cast<const V*>(M.inv_diag) : nullptr;
+        P.sc = scal.as<V>();
+        P.st = this->st();
+        P.stop_status = this->stat();
+        P.hist = this->hist.template as<V>();
+        P.factor = static_cast<V>(stop.reduction_factor);
+        P.max_iters = stop.max_iters;
+        P.ws = bigws.p;
+        return P;
+    }
+
+    int allreduce(cudaStream_t s, V* buf, size_t count)
+    {
+        gkob200_dist_comm* c = dm->comm;
+        if (!c || c->size == 1) return 0;
+        GKOB200_NCCL(ncclAllReduce(buf, buf, count, nccl_type<V>(), ncclSum, c->comm, s));
+        ++launch_count;
+        return 0;
+    }
+
+    template <bool First>
+    int update(cudaStream_t s, V* x)
+    {
+        DistCgParams<V> P = params(x);
+        const int grid = grid_for(n, 256, 6);
+        if (M.kind == GKOB200_PRECOND_NONE)
+            dist_cg_update<V, 0, First><<<grid, 256, 0, s>>>(P);
+        else
+            dist_cg_update<V, 1, First><<<grid, 256, 0, s>>>(P);
+        GKOB200_CHECK_LAUNCH();
+        int rc = allreduce(s, P.sc + D_RED0, 2);
+        if (rc) return rc;
+        dist_cg_scalars<V, First><<<1, 1, 0, s>>>(P);
+        launch_count += 2;
+        GKOB200_CHECK_LAUNCH();
+        return 0;
+    }
+
+    int apply(cudaStream_t s, const void* b_, int64_t bs, void* x_, int64_t xs) override
+    {
+        const V* b = static_cast<const V*>(b_);
+        V* x = static_cast<V*>(x_);
+        launch_count = 0;
+        this->num_iterations = 0;
+        dm->launches = 0;
+        if (bs != 1 || xs != 1) return GKOB200_EUNSUPPORTED;
+        DistCgParams<V> P = params(x);
+        int rc;
+        if ((rc = this->reset_state(s))) return rc;
+        // r = b ; r = -A x + r ; baseline norm (sum of local squared norms, then sqrt:
+        // core/distributed/vector.cpp:394-407)
+        if ((rc = typed::dense_copy(B::tag(), s, n, int64_t(1), b, int64_t(1), P.r, int64_t(1)))) return rc;
+        if ((rc = typed::dense_fill(B::tag(), s, int64_t(1), int64_t(1), P.sc + D_RHO, int64_t(1), V(0)))) return rc;
+        if ((rc = typed::dense_fill(B::tag(), s, int64_t(1), int64_t(1), P.sc + D_PREV_RHO, int64_t(1), V(1)))) return rc;
+        if ((rc = dist_apply<V>(dm, s, x, 1, 1, this->neg_one(), this->one(), P.r, 1, nullptr))) return rc;
+        launch_count += 3;
+        if (stop.baseline == GKOB200_STOP_ABSOLUTE) {
+            set_one<V><<<1, 1, 0, s>>>(P.sc + D_ORIG_TAU);
+        } else {
+            const V* src = stop.baseline == GKOB200_STOP_RHS_NORM ? b : P.r;
+            sq_norm_partial<V><<<grid_for(n, 256, 4), 256, 0, s>>>(n, src, P.sc + D_RED0, bigws.p);
+            if ((rc = allreduce(s, P.sc + D_RED0, 1))) return rc;
+            sqrt_to<V><<<1, 1, 0, s>>>(P.sc + D_ORIG_TAU, P.sc + D_RED0);
+            launch_count += 2;
+        }
+        GKOB200_CHECK_LAUNCH();
+        if ((rc = update<true>(s, x))) return rc;
+        int64_t it = 0;
+        bool stopped = false;
+        const int grid = grid_for(n, 256, 6);
+        while (true) {
+            if (it % this->chunk == 0 || it >= stop.max_iters) {
+                if ((rc = this->poll(s, &stopped))) return rc;
+                if (stopped) break;
+            }
+            if (M.kind == GKOB200_PRECOND_NONE)
+                dist_cg_direction<V, true><<<grid, 256, 0, s>>>(P);
+            else
+                dist_cg_direction<V, false><<<grid, 256, 0, s>>>(P);
+            ++launch_count;
+            GKOB200_CHECK_LAUNCH();
+            SpmvFusion<V> fu;
+            fu.skip = &this->st()->stopped;
+            fu.w = P.p;
+            fu.out = P.sc + D_BETA;
+            fu.ws = bigws.p;
+            fu.ws_blocks = ws_blocks;
+            if ((rc = dist_apply<V>(dm, s, P.p, 1, 1, nullptr, nullptr, P.q, 1, &fu))) return rc;
+            if ((rc = allreduce(s, P.sc + D_BETA, 1))) return rc;
+            if ((rc = update<false>(s, x))) return rc;
+            ++it;
+        }
+        launch_count += dm->launches;
+        return this->finish(s);
+    }
+};
+
+}  // namespace
+}  // namespace gkob200
+
+using namespace gkob200;
+
+extern "C" {
+
+int gkob200_nccl_unique_id(void* out128)
+{
+    if (!out128) return GKOB200_EINVAL;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    ncclUniqueId id;
+    GKOB200_NCCL(ncclGetUniqueId(&id));
+    memcpy(out128, &id, sizeof(id));
+    return 0;
+}
+
+int gkob200_dist_comm_create(const void* id128, int rank, int size, gkob200_dist_comm** out)
+{
+    if (!out || rank < 0 || size < 1 || rank >= size) return GKOB200_EINVAL;
+    auto* c = new gkob200_dist_comm();
+    c->rank = rank;
+    c->size = size;
+    if (size > 1) {
+        if (!id128) {
+            delete c;
+            return GKOB200_EINVAL;
+        }
+        ncclUniqueId id;
+        memcpy(&id, id128, sizeof(id));
+        ncclResult_t r = ncclCommInitRank(&c->comm, size, id, rank);
+        if (r != ncclSuccess) {
+            delete c;
+            return 1000 + static_cast<int>(r);
+        }
+    }
+    cudaError_t e = cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete c;
+        return static_cast<int>(e);
+    }
+    *out = c;
+    return 0;
+}
+
+int gkob200_dist_comm_destroy(gkob200_dist_comm* c)
+{
+    if (!c) return 0;
+    if (c->comm) ncclCommDestroy(c->comm);
+    if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+    delete c;
+    return 0;
+}
+
+int gkob200_dist_comm_rank(const gkob200_dist_comm* c) { return c ? c->rank : -1; }
+int gkob200_dist_comm_size(const gkob200_dist_comm* c) { return c ? c->size : -1; }
+
+/* in-place sum all-reduce of `count` values on `stream` (distributed::Vector reductions) */
+int gkob200_dist_allreduce_sum_f64(gkob200_dist_comm* c, void* stream, double* buf, int64_t count)
+{
+    if (!c || count < 0) return GKOB200_EINVAL;
+    if (c->size == 1 || count == 0) return 0;
+    GKOB200_NCCL(ncclAllReduce(buf, buf, static_cast<size_t>(count), ncclDouble, ncclSum, c->comm, as_stream(stream)));
+    return 0;
+}
+int gkob200_dist_allreduce_sum_f32(gkob200_dist_comm* c, void* stream, float* buf, int64_t count)
+{
+    if (!c || count < 0) return GKOB200_EINVAL;
+    if (c->size == 1 || count == 0) return 0;
+    GKOB200_NCCL(ncclAllReduce(buf, buf, static_cast<size_t>(count), ncclFloat, ncclSum, c->comm, as_stream(stream)));
+    return 0;
+}
+/* all-to-all of `count` int64 per peer (device buffers): setup exchange of halo sizes */
+int gkob200_dist_alltoall_i64(gkob200_dist_comm* c, void* stream, const int64_t* send, int64_t* recv, int64_t count)
+{
+    if (!c || !send || !recv || count < 0) return GKOB200_EINVAL;
+    cudaStream_t s = as_stream(stream);
+    if (c->size == 1) {
+        GKOB200_CUDA(cudaMemcpyAsync(recv, send, sizeof(int64_t) * count, cudaMemcpyDeviceToDevice, s));
+        return 0;
+    }
+    GKOB200_NCCL(ncclGroupStart());
+    for (int p = 0; p < c->size; ++p) {
+        GKOB200_NCCL(ncclSend(send + p * count, static_cast<size_t>(count), ncclInt64, p, c->comm, s));
+        GKOB200_NCCL(ncclRecv(recv + p * count, static_cast<size_t>(count), ncclInt64, p, c->comm, s));
+    }
+    GKOB200_NCCL(ncclGroupEnd());
+    return 0;
+}
+/* all-to-all-v of int32 (device buffers): gather indices travel from receivers to senders
+ * [ref: core/distributed/matrix.cpp:218-221] */
+int gkob200_dist_alltoallv_i32(gkob200_dist_comm* c, void* stream, const int32_t* send, const int64_t* send_sizes_host,
+                               const int64_t* send_offsets_host, int32_t* recv, const int64_t* recv_sizes_host,
+                               const int64_t* recv_offsets_host)
+{
+    if (!c) return GKOB200_EINVAL;
+    cudaStream_t s = as_stream(stream);
+    if (c->size == 1) {
+        if (send_sizes_host[0] > 0)
+            GKOB200_CUDA(cudaMemcpyAsync(recv + recv_offsets_host[0], send + send_offsets_host[0],
+                                         sizeof(int32_t) * send_sizes_host[0], cudaMemcpyDeviceToDevice, s));
+        return 0;
+    }
+    GKOB200_NCCL(ncclGroupStart());
+    for (int p = 0; p < c->size; ++p) {
+        if (send_sizes_host[p] > 0)
+            GKOB200_NCCL(ncclSend(send + send_offsets_host[p], static_cast<size_t>(send_sizes_host[p]), ncclInt32, p, c->comm, s));
+        if (recv_sizes_host[p] > 0)
+            GKOB200_NCCL(ncclRecv(recv + recv_offsets_host[p], static_cast<size_t>(recv_sizes_host[p]), ncclInt32, p, c->comm, s));
+    }
+    GKOB200_NCCL(ncclGroupEnd());
+    return 0;
+}
+
+int gkob200_dist_matrix_create(gkob200_dist_comm* comm, const gkob200_matrix* local, const gkob200_matrix* non_local,
+                               const int32_t* gather_idxs, const int64_t* send_sizes_host,
+                               const int64_t* recv_sizes_host, gkob200_dist_matrix** out)
+{
+    if (!comm || !local || !out || !send_sizes_host || !recv_sizes_host) return GKOB200_EINVAL;
+    auto* m = new gkob200_dist_matrix();
+    m->comm = comm;
+    m->local = *local;
+    if (non_local) m->non_local = *non_local;
+    m->gather_idxs = gather_idxs;
+    const int P = comm->size;
+    m->send_sizes.assign(send_sizes_host, send_sizes_host + P);
+    m->recv_sizes.assign(recv_sizes_host, recv_sizes_host + P);
+    m->send_offsets.assign(P + 1, 0);
+    m->recv_offsets.assign(P + 1, 0);
+    for (int p = 0; p < P; ++p) {
+        m->send_offsets[p + 1] = m->send_offsets[p] + m->send_sizes[p];
+        m->recv_offsets[p + 1] = m->recv_offsets[p] + m->recv_sizes[p];
+    }
+    m->send_total = m->send_offsets[P];
+    m->recv_total = m->recv_offsets[P];
+    if (cudaEventCreateWithFlags(&m->packed, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->received, cudaEventDisableTiming) != cudaSuccess) {
+        delete m;
+        return static_cast<int>(cudaGetLastError());
+    }
+    *out = m;
+    return 0;
+}
+
+int gkob200_dist_matrix_destroy(gkob200_dist_matrix* m)
+{
+    if (!m) return 0;
+    if (m->packed) cudaEventDestroy(m->packed);
+    if (m->received) cudaEventDestroy(m->received);
+    delete m;
+    return 0;
+}
+
+int gkob200_dist_matrix_apply(gkob200_dist_matrix* m, void* stream, const void* b, int64_t b_stride, int64_t nrhs,
+                              const void* alpha, const void* beta, void* x, int64_t x_stride)
+{
+    if (!m || (alpha == nullptr) != (beta == nullptr)) return GKOB200_EINVAL;
+    if (m->local.value_type == GKOB200_F64)
+        return dist_apply<double>(m, as_stream(stream), static_cast<const double*>(b), b_stride, nrhs,
+                                  static_cast<const double*>(alpha), static_cast<const double*>(beta),
+                                  static_cast<double*>(x), x_stride, nullptr);
+    return dist_apply<float>(m, as_stream(stream), static_cast<const float*>(b), b_stride, nrhs,
+                             static_cast<const float*>(alpha), static_cast<const float*>(beta), static_cast<float*>(x),
+                             x_stride, nullptr);
+}
+
+int gkob200_dist_solver_create(int kind, gkob200_dist_matrix* A, const gkob200_precond* M, const gkob200_stop* stop,
+                               int64_t nrhs, gkob200_solver** out)
+{
+    if (!A || !stop || !out) return GKOB200_EINVAL;
+    *out = nullptr;
+    if (kind != GKOB200_SOLVER_CG) return GKOB200_EUNSUPPORTED;
+    int rc;
+    if (A->local.value_type == GKOB200_F64) {
+        auto* s = new DistCgSolver<double>();
+        s->dm = A;
+        if (M) s->M = *M; else { s->M = gkob200_precond{}; s->M.kind = GKOB200_PRECOND_NONE; }
+        s->stop = *stop;
+        s->k = nrhs;
+        s->nrhs = nrhs;
+        if ((rc = s->init())) { delete s; return rc; }
+        *out = s;
+    } else {
+        auto* s = new DistCgSolver<float>();
+        s->dm = A;
+        if (M) s->M = *M; else { s->M = gkob200_precond{}; s->M.kind = GKOB200_PRECOND_NONE; }
+        s->stop = *stop;
+        s->k = nrhs;
+        s->nrhs = nrhs;
+        if ((rc = s->init())) { delete s; return rc; }
+        *out = s;
+    }
+    return 0;
+}
+
+}  // extern "C"
