@@ -29,7 +29,11 @@ enum gkob200_format {
     GKOB200_FMT_ELL = 1,    /* col_idxs/values[ell_stride*ell_width] column-major, pad col = -1    */
     GKOB200_FMT_SELLP = 2,  /* slice_sets[ns+1] (uint64), slice_lengths[ns] (uint64), slice_size   */
     GKOB200_FMT_COO = 3,    /* row_idxs in row_ptrs, col_idxs, values, all [nnz], row-sorted       */
-    GKOB200_FMT_HYBRID = 4  /* ELL part in the ell_* fields + COO part in the coo_* fields         */
+    GKOB200_FMT_HYBRID = 4, /* ELL part in the ell_* fields + COO part in the coo_* fields         */
+    GKOB200_FMT_CSR_ROWS = 5 /* CSR over the listed rows only: row_list[n_listed] (int32, increasing),
+                                row_ptrs[n_listed+1]; apply ACCUMULATES into the listed rows
+                                (c[row] = beta*c[row] + alpha*sum).  Used for the non-local block of
+                                the distributed matrix, whose rows are empty except at the slab faces */
 };
 
 /* Borrowed description of a sparse matrix living on the current device
@@ -61,6 +65,9 @@ typedef struct gkob200_matrix {
     /* scratch for kernels that need it (merge-path carries); may be NULL if unused */
     void* workspace;
     size_t workspace_bytes;
+    /* CSR_ROWS */
+    const int32_t* row_list;
+    int64_t n_listed;
 } gkob200_matrix;
 
 /* c = A b  /  c = alpha A b + beta c  for any format of the descriptor

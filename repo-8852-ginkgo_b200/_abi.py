@@ -14,7 +14,7 @@ REDUCE_WS_BYTES = 256 + 148 * 16 * 8 * 8
 CSR_CLASSICAL, CSR_MERGE_PATH, CSR_AUTO = 0, 1, 2
 F64, F32 = 0, 1
 I32, I64 = 0, 1
-FMT_CSR, FMT_ELL, FMT_SELLP, FMT_COO, FMT_HYBRID = range(5)
+FMT_CSR, FMT_ELL, FMT_SELLP, FMT_COO, FMT_HYBRID, FMT_CSR_ROWS = range(6)
 PRECOND_NONE, PRECOND_JACOBI_SCALAR, PRECOND_JACOBI_BLOCK = range(3)
 STOP_RHS_NORM, STOP_INITIAL_RESNORM, STOP_ABSOLUTE = range(3)
 SOLVER_CG, SOLVER_BICGSTAB, SOLVER_GMRES = range(3)
@@ -31,6 +31,7 @@ class Matrix(C.Structure):
         ("slice_sets", vp), ("slice_lengths", vp),
         ("coo_nnz", i64), ("coo_row_idxs", vp), ("coo_col_idxs", vp), ("coo_values", vp),
         ("workspace", vp), ("workspace_bytes", sz),
+        ("row_list", vp), ("n_listed", i64),
     ]
 
 

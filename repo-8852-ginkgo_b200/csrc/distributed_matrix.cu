@@ -122,13 +122,20 @@ int dist_apply(gkob200_dist_matrix* m, cudaStream_t s, const V* b, int64_t bs, i
     }
     const bool nl = has_halo && m->recv_total > 0 && m->non_local.nnz > 0;
     // local block (overlaps the halo exchange)
-    SpmvFusion<V> fl;
+    // With a row-compressed non-local block the dot w.(A b) is split: the local SpMV
+    // reduces w.(A_loc b) into out[0], the non-local kernel its own contribution into out[1]
+    // (the caller adds the two after the all-reduce).  With a full-height non-local CSR the
+    // dot is taken once, by the non-local SpMV, on the final result.
+    const bool split = nl && m->non_local.format == GKOB200_FMT_CSR_ROWS;
+    SpmvFusion<V> fl, fn;
     if (fusion) {
         fl = *fusion;
-        if (nl) {  // the dot belongs to the final result: computed by the non-local SpMV
+        fn = *fusion;
+        if (nl && !split) {
             fl.w = nullptr;
             fl.out = nullptr;
         }
+        if (split && fn.out) fn.out = fn.out + 1;
     }
     if ((rc = matrix_apply<V>(s, m->local, b, bs, nrhs, alpha, beta, x, xs, fusion ? &fl : nullptr))) return rc;
     ++m->launches;
@@ -136,14 +143,18 @@ int dist_apply(gkob200_dist_matrix* m, cudaStream_t s, const V* b, int64_t bs, i
     if (nl) {
         // x += alpha * A_nl * ghost   (reference: non_local_mtx_->apply(alpha|one, recv, one, x))
         const V* one = m->consts.as<V>();
-        if ((rc = matrix_apply<V>(s, m->non_local, recv, nrhs, nrhs, alpha ? alpha : one, one, x, xs, fusion))) return rc;
+        if ((rc = matrix_apply<V>(s, m->non_local, recv, nrhs, nrhs, alpha ? alpha : one, one, x, xs,
+                                  fusion ? &fn : nullptr)))
+            return rc;
         ++m->launches;
+    } else if (fusion && fusion->out && nrhs == 1) {
+        GKOB200_CUDA(cudaMemsetAsync(fusion->out + 1, 0, sizeof(V), s));
     }
     return 0;
 }
 
 // ------------------------------- distributed CG --------------------------------
-enum { D_RHO = 0, D_PREV_RHO, D_BETA, D_TAU, D_ORIG_TAU, D_RED0, D_RED1, D_COUNT };
+enum { D_RHO = 0, D_PREV_RHO, D_BETA, D_BETA2, D_TAU, D_ORIG_TAU, D_RED0, D_RED1, D_COUNT };
 
 template <typename V>
 struct DistCgParams {
@@ -167,7 +178,7 @@ __global__ void __launch_bounds__(256) dist_cg_update(DistCgParams<V> P)
     V t = V(0);
     bool upd = false;
     if (!First) {
-        const V beta = P.sc[D_BETA];
+        const V beta = P.sc[D_BETA] + P.sc[D_BETA2];  // local + non-local share of p.q
         upd = beta != V(0);
         if (upd) t = div_rn(P.sc[D_RHO], beta);
     }
@@ -354,7 +365,7 @@ struct DistCgSolver : SolverBase<V> {
             fu.ws = bigws.p;
             fu.ws_blocks = ws_blocks;
             if ((rc = dist_apply<V>(dm, s, P.p, 1, 1, nullptr, nullptr, P.q, 1, &fu))) return rc;
-            if ((rc = allreduce(s, P.sc + D_BETA, 1))) return rc;
+            if ((rc = allreduce(s, P.sc + D_BETA, 2))) return rc;
             if ((rc = update<false>(s, x))) return rc;
             ++it;
         }

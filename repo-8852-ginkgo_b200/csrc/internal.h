@@ -41,6 +41,12 @@ int coo_spmv_launch(cudaStream_t s, int64_t n_rows, int64_t nnz, const I* rows, 
                     const V* b, int64_t b_stride, int64_t nrhs, const V* alpha, const V* beta, bool accumulate,
                     V* c, int64_t c_stride, void* workspace, size_t workspace_bytes);
 
+// c[row] = beta c[row] + alpha (A b)[row] on the listed rows only (alpha, beta required)
+template <typename V, typename I>
+int csr_rows_spmv_launch(cudaStream_t s, int64_t n_listed, const int32_t* row_list, const I* row_ptrs, const I* cols,
+                         const V* vals, const V* b, int64_t b_stride, int64_t nrhs, const V* alpha, const V* beta,
+                         V* c, int64_t c_stride, const SpmvFusion<V>* fusion);
+
 // y = A x (alpha == beta == nullptr) or y = alpha A x + beta y, any format.
 template <typename V>
 int matrix_apply(cudaStream_t s, const gkob200_matrix& A, const V* b, int64_t b_stride, int64_t nrhs,

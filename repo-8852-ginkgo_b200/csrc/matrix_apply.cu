@@ -15,7 +15,7 @@ bool matrix_apply_fuses_dot(const gkob200_matrix& A, int64_t nrhs)
                            : GKOB200_CSR_MERGE_PATH;
         return strategy == GKOB200_CSR_CLASSICAL;
     }
-    return A.format == GKOB200_FMT_ELL || A.format == GKOB200_FMT_SELLP;
+    return A.format == GKOB200_FMT_ELL || A.format == GKOB200_FMT_SELLP || A.format == GKOB200_FMT_CSR_ROWS;
 }
 
 template <typename V>
@@ -59,6 +59,12 @@ int matrix_apply(cudaStream_t s, const gkob200_matrix& A, const V* b, int64_t b_
                                            c_stride, strategy, A.csr_max_block_nnz, A.workspace,
                                            A.workspace_bytes, nrhs == 1 ? fp : nullptr);
     }
+    case GKOB200_FMT_CSR_ROWS:
+        if (A.index_type != GKOB200_I32 || !alpha) return GKOB200_EUNSUPPORTED;
+        return csr_rows_spmv_launch<V, int32_t>(s, A.n_listed, A.row_list, static_cast<const int32_t*>(A.row_ptrs),
+                                                static_cast<const int32_t*>(A.col_idxs),
+                                                static_cast<const V*>(A.values), b, b_stride, nrhs, alpha, beta, c,
+                                                c_stride, fusion);
     case GKOB200_FMT_ELL:
         if (A.index_type == GKOB200_I32)
             return ell_spmv_launch<V, int32_t>(s, A.n_rows, A.ell_stride, A.ell_width,

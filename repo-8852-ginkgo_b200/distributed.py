@@ -168,6 +168,44 @@ def _coo_to_csr(exec_, n_rows, n_cols, rows, cols, vals, strategy):
     return Csr(exec_, (n_rows, n_cols), rp, cols, vals, strategy)
 
 
+class CsrRows(_SparseBase):
+    """Row-compressed CSR (GKOB200_FMT_CSR_ROWS): only the rows that have entries are stored.
+    The non-local block of a slab-partitioned stencil has entries on the two slab faces only
+    (2 x 40 000 of 8 000 000 rows at 200^3), so a full-height CSR pass over it would cost more
+    than the halo itself.  apply() accumulates: x[row] = beta x[row] + alpha (A b)[row]."""
+
+    def __init__(self, exec_, size, rows_coo, cols, vals):
+        self.exec, self.size = exec_, tuple(size)
+        dev = exec_.device
+        if rows_coo.numel():
+            uniq, counts = torch.unique_consecutive(rows_coo, return_counts=True)
+        else:
+            uniq = torch.zeros(0, dtype=torch.int32, device=dev)
+            counts = torch.zeros(0, dtype=torch.int64, device=dev)
+        self.row_list = uniq.to(torch.int32).contiguous()
+        self.row_ptrs = torch.zeros(uniq.numel() + 1, dtype=torch.int32, device=dev)
+        if uniq.numel():
+            self.row_ptrs[1:] = torch.cumsum(counts, 0).to(torch.int32)
+        self.col_idxs, self.values = cols, vals
+        self.nnz = int(vals.numel())
+        self.V = vname(vals.dtype)
+
+    def descriptor(self):
+        d = _abi.Matrix()
+        d.format = _abi.FMT_CSR_ROWS
+        d.value_type = _abi.F64 if self.V == "f64" else _abi.F32
+        d.index_type = _abi.I32
+        d.n_rows, d.n_cols = self.size
+        d.nnz = self.nnz
+        d.row_ptrs, d.col_idxs, d.values = self.row_ptrs.data_ptr(), self.col_idxs.data_ptr(), self.values.data_ptr()
+        d.row_list, d.n_listed = self.row_list.data_ptr(), self.row_list.numel()
+        return d
+
+    def spmv_bytes(self, nrhs=1):
+        v = self.values.element_size()
+        return self.nnz * (v + 4) + self.row_list.numel() * (8 + 2 * nrhs * v) + self.size[1] * nrhs * v
+
+
 def halo_plan(comm, recv_sizes, recv_gather_idxs):
     """The two exchanges of read_distributed (reference core/distributed/matrix.cpp:197-221):
     step 1: all_to_all of one count per peer turns recv_sizes into send_sizes; step 2: all_to_all_v
@@ -201,7 +239,8 @@ class Matrix(_SparseBase):
         n_loc_rows, n_loc_cols = row_part.get_part_size(comm.rank), col_part.get_part_size(comm.rank)
         n_ghost = parts["gather"].numel()
         self.local = _coo_to_csr(exec_, n_loc_rows, n_loc_cols, parts["lrow"], parts["lcol"], parts["lval"], "automatical")
-        self.non_local = _coo_to_csr(exec_, n_loc_rows, n_ghost, parts["nrow"], parts["ncol"], parts["nval"], "classical")
+        # non-local block: same entries as the reference's Csr non_local_mtx_, stored row-compressed
+        self.non_local = CsrRows(exec_, (n_loc_rows, n_ghost), parts["nrow"], parts["ncol"], parts["nval"])
         self.non_local_to_global = parts["nl_to_global"]
         self.send_sizes, self.recv_sizes, self.gather_idxs = halo_plan(comm, parts["recv_sizes"], parts["gather"])
         self._ld, self._nd = self.local.descriptor(), self.non_local.descriptor()
