@@ -44,7 +44,7 @@ extern "C" {
 /* Bytes of zero-initialised device scratch every reducing kernel needs
  * (ticket + per-block partial sums).  Initialise once with
  * gkob200_reduce_ws_init; kernels leave it re-armed. */
-#define GKOB200_REDUCE_WS_BYTES (256 + 148 * 16 * 8 * 8)
+#define GKOB200_REDUCE_WS_BYTES (1024 + (148 * 16 + 256) * 8 * 8)
 
 int gkob200_version(void);
 /* Number of SMs of the current device (blocking, cached). */

@@ -9,7 +9,7 @@ VT = {"f64": f64, "f32": f32}
 
 # error codes
 EINVAL, EUNSUPPORTED, EWORKSPACE = -1, -2, -3
-REDUCE_WS_BYTES = 256 + 148 * 16 * 8 * 8
+REDUCE_WS_BYTES = 1024 + (148 * 16 + 256) * 8 * 8
 
 CSR_CLASSICAL, CSR_MERGE_PATH, CSR_AUTO = 0, 1, 2
 F64, F32 = 0, 1

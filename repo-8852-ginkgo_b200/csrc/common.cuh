@@ -103,13 +103,19 @@ __device__ __forceinline__ T block_sum(T v, T* red)
 
 // Single-pass deterministic grid reduction of NV running sums.
 //
-// Every block leaves its NV block-sums in `partials[blockIdx.x*NV + i]`, then
-// takes a ticket; the block that draws the last ticket re-reads all partials in
-// a fixed order (independent of which block happens to be last), reduces them
-// and hands the NV totals to `fin(totals)` on its thread 0, then re-arms the
-// ticket.  One launch, no atomics on data, run-to-run bit-reproducible for a
-// fixed grid size.  (The reference needs two launches + a tmp array:
-// common/cuda_hip/base/kernel_launch_reduction.hpp.inc:33-330.)
+// Every block leaves its NV block-sums in `partials[blockIdx.x*NV + i]`, then takes a
+// ticket; the block that draws the last ticket re-reads the partials in a fixed order
+// (independent of which block happens to be last), reduces them and hands the NV totals
+// to `fin(totals)` on its thread 0, then re-arms the ticket.  One launch, no atomics on
+// data, run-to-run bit-reproducible for a fixed grid size.  (The reference needs two
+// launches + a tmp array: common/cuda_hip/base/kernel_launch_reduction.hpp.inc:33-330.)
+//
+// Large grids (the SpMV with a fused dot runs one CTA per 128 rows: 62 500 CTAs at 200^3)
+// use TWO ticket levels — groups of >= 1024 CTAs, then the groups — because tens of
+// thousands of atomics on one address serialise in L2 (measured: +100 us per launch).
+constexpr unsigned kTicketGroup = 1024;
+constexpr unsigned kMaxTicketGroups = 255;  // ticket words 1..255 of the 1 KB header
+
 template <int NV, typename T, typename Fin>
 __device__ __forceinline__ void grid_reduce(T (&v)[NV], T* partials, unsigned* ticket, Fin fin)
 {
@@ -120,10 +126,56 @@ __device__ __forceinline__ void grid_reduce(T (&v)[NV], T* partials, unsigned* t
         T s = block_sum(v[i], red);
         if (threadIdx.x == 0) partials[static_cast<size_t>(blockIdx.x) * NV + i] = s;
     }
+    const unsigned grid = gridDim.x;
+    if (grid <= kTicketGroup) {
+        if (threadIdx.x == 0) {
+            __threadfence();
+            is_last = (atomicAdd(ticket, 1u) == grid - 1);
+        }
+        __syncthreads();
+        if (!is_last) return;
+        __threadfence();
+        T tot[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            T s = T(0);
+            for (unsigned b = threadIdx.x; b < grid; b += blockDim.x)
+                s += __ldcg(&partials[static_cast<size_t>(b) * NV + i]);
+            tot[i] = block_sum(s, red);
+        }
+        if (threadIdx.x == 0) {
+            *ticket = 0u;
+            fin(tot);
+        }
+        return;
+    }
+    // ---- two levels ---------------------------------------------------------------
+    unsigned gsize = (grid + kMaxTicketGroups - 1) / kMaxTicketGroups;
+    if (gsize < kTicketGroup) gsize = kTicketGroup;
+    const unsigned ngroups = (grid + gsize - 1) / gsize;
+    const unsigned g = blockIdx.x / gsize;
+    const unsigned gbegin = g * gsize;
+    const unsigned gend = gbegin + gsize < grid ? gbegin + gsize : grid;
     if (threadIdx.x == 0) {
         __threadfence();
-        unsigned t = atomicAdd(ticket, 1u);
-        is_last = (t == gridDim.x - 1);
+        is_last = (atomicAdd(ticket + 1 + g, 1u) == gend - gbegin - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        T s = T(0);
+        for (unsigned b = gbegin + threadIdx.x; b < gend; b += blockDim.x)
+            s += __ldcg(&partials[static_cast<size_t>(b) * NV + i]);
+        s = block_sum(s, red);
+        if (threadIdx.x == 0) partials[static_cast<size_t>(grid + g) * NV + i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ticket[1 + g] = 0u;
+        __threadfence();
+        is_last = (atomicAdd(ticket, 1u) == ngroups - 1);
     }
     __syncthreads();
     if (!is_last) return;
@@ -132,8 +184,8 @@ __device__ __forceinline__ void grid_reduce(T (&v)[NV], T* partials, unsigned* t
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         T s = T(0);
-        for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x)
-            s += __ldcg(&partials[static_cast<size_t>(b) * NV + i]);
+        for (unsigned b = threadIdx.x; b < ngroups; b += blockDim.x)
+            s += __ldcg(&partials[static_cast<size_t>(grid + b) * NV + i]);
         tot[i] = block_sum(s, red);
     }
     if (threadIdx.x == 0) {
@@ -142,19 +194,27 @@ __device__ __forceinline__ void grid_reduce(T (&v)[NV], T* partials, unsigned* t
     }
 }
 
-// Scratch carried by every reducing kernel: a ticket word followed by partials.
-// Layout of a `gkob200` reduction workspace (bytes): [0,256) ticket(s),
-// [256, ...) partial sums.  GKOB200_REDUCE_WS_BYTES is large enough for the
-// largest grid any kernel here launches (<= 148*16 blocks) times 8 values.
+// Scratch carried by every reducing kernel: ticket words followed by partials.
+// Layout of a reduction workspace (bytes): [0,1024) tickets, [1024, ...) partial sums.
+// GKOB200_REDUCE_WS_BYTES covers the largest grid the BLAS-1 kernels launch
+// (<= 148*16 blocks) times 8 values; solvers that fuse a dot into the SpMV allocate
+// reduce_ws_bytes(blocks) for that grid.
+constexpr int kReduceHeader = 1024;
 constexpr int kReduceMaxBlocks = 148 * 16;
 constexpr int kReduceMaxVals = 8;
-static_assert(GKOB200_REDUCE_WS_BYTES >= 256 + kReduceMaxBlocks * kReduceMaxVals * 8, "ws");
+static_assert(GKOB200_REDUCE_WS_BYTES >= kReduceHeader + (kReduceMaxBlocks + 256) * kReduceMaxVals * 8, "ws");
+
+// bytes for a grid of `blocks` CTAs (+ room for the group partials of the second level)
+inline size_t reduce_ws_bytes(int64_t blocks)
+{
+    return static_cast<size_t>(kReduceHeader) + static_cast<size_t>(blocks + 256) * kReduceMaxVals * sizeof(double);
+}
 
 __host__ __device__ inline unsigned* ws_ticket(void* ws) { return reinterpret_cast<unsigned*>(ws); }
 template <typename T>
 __host__ __device__ inline T* ws_partials(void* ws)
 {
-    return reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + 256);
+    return reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + kReduceHeader);
 }
 
 }  // namespace gkob200

@@ -265,7 +265,7 @@ struct DistCgSolver : SolverBase<V> {
         if ((rc = scal.alloc(D_COUNT * sizeof(V)))) return rc;
         ws_blocks = ceildiv(n, 128) + 1;
         if (ws_blocks < kReduceMaxBlocks) ws_blocks = kReduceMaxBlocks;
-        return bigws.alloc(256 + static_cast<size_t>(ws_blocks) * kReduceMaxVals * sizeof(double));
+        return bigws.alloc(reduce_ws_bytes(ws_blocks));
     }
 
     DistCgParams<V> params(V* x)

@@ -198,7 +198,7 @@ struct CgSolver : gkob200_solver {
         // kernel launches (the SpMV with the fused dot runs one CTA per 128 rows)
         ws_blocks = ceildiv(n, 128) + 1;
         if (ws_blocks < kReduceMaxBlocks) ws_blocks = kReduceMaxBlocks;
-        if ((rc = ws.alloc(256 + static_cast<size_t>(ws_blocks) * kReduceMaxVals * sizeof(double)))) return rc;
+        if ((rc = ws.alloc(reduce_ws_bytes(ws_blocks)))) return rc;
         GKOB200_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h_state), 2 * sizeof(SolverState), cudaHostAllocDefault));
         for (auto& e : ev) GKOB200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         GKOB200_CUDA(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
