@@ -69,7 +69,11 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t_mark = index, [], None, 0.0
+
+    def mark(self):
+        """Samples taken before this call (set-up, warm-up) are dropped."""
+        self.t_mark = time.time()
 
     def start(self):
         try:
@@ -83,7 +87,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if not self.proc:
@@ -95,8 +99,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) < 6:
+        for ts, r in self.rows:
+            if len(r) < 6 or ts < self.t_mark:
                 continue
             try:
                 sm.append(float(r[0]))
@@ -226,10 +230,11 @@ def main():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) * 1e-3, launches
 
-    for _ in range(max(args.warmup, 3)):
-        step_device()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler.mark()
     secs, launches = timed(step_device, args.steps)
     clocks = sampler.stop()
     assert solver.num_iterations == iters, solver.num_iterations

@@ -10,9 +10,17 @@ import numpy as np
 
 
 def run_distributed(args, gko, rank, world, local_rank):
+    import sys
     import torch
     import torch.distributed as dist
     from bench import METRIC, UNIT, ClockSampler, cg_model_bytes, peaks
+    # NCCL prints its version banner on stdout; the contract is ONE JSON line on stdout.
+    # Everything goes to stderr until rank 0 writes the result line to the saved descriptor.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sampler = ClockSampler(local_rank)
+    sampler.start()          # nvidia-smi needs ~1 s to come up: start it before the set-up
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     D = gko.distributed
@@ -63,8 +71,7 @@ def run_distributed(args, gko, rank, world, local_rank):
 
     for _ in range(max(args.warmup, 3)):
         step_device()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark()
     secs, launches = timed(step_device, args.steps)
     clocks = sampler.stop()
     assert solver.num_iterations == iters
@@ -105,6 +112,6 @@ def run_distributed(args, gko, rank, world, local_rank):
             "cg_iteration": {"us": 1e6 * secs / (args.steps * iters), "model_bytes_per_gpu": it_bytes,
                              "model_gbs_per_gpu": it_bytes * args.steps * iters / secs / 1e9},
         }
-        print(json.dumps(line), flush=True)
+        os.write(saved_stdout, (json.dumps(line) + "\n").encode())
     dist.barrier()
     dist.destroy_process_group()

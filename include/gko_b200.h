@@ -50,6 +50,9 @@ int gkob200_version(void);
 /* Number of SMs of the current device (blocking, cached). */
 int gkob200_sm_count(void);
 int gkob200_reduce_ws_init(void* stream, void* ws);
+/* components::fill_array for elements of 1/2/4/8 bytes; the value is read from the HOST
+ * [ref: core/components/fill_array_kernels.hpp] */
+int gkob200_fill_array(void* stream, void* data, int64_t n, int elem_bytes, const void* value_host);
 
 /* ------------------------------------------------------------------------- *
  * CSR SpMV / SpMM

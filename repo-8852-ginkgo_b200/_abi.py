@@ -59,6 +59,7 @@ def declare(lib):
     d("gkob200_version", [])
     d("gkob200_sm_count", [])
     d("gkob200_reduce_ws_init", [vp, vp])
+    d("gkob200_fill_array", [vp, vp, i64, C.c_int, vp])
     for I in ("i32", "i64"):
         d(f"gkob200_csr_row_stats_{I}", [vp, i64, vp, vp])
     d("gkob200_csr_pick_strategy", [i64, i64, i64, i64])

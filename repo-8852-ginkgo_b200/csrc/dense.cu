@@ -6,6 +6,8 @@
 // Reductions are single-launch (ticketed grid reduction) and bit-reproducible.
 // Algorithmic bytes (reference models benchmark/blas/blas.cpp:97-140): copy 2n,
 // axpy 3n, scal 2n, dot 2n, norm n values.
+#include <cstring>
+
 #include "launch.cuh"
 
 namespace gkob200 {
@@ -123,6 +125,26 @@ int max_smem_optin()
 using namespace gkob200;
 
 extern "C" {
+
+/* components::fill_array for any trivially copyable element of 1/2/4/8 bytes
+ * [ref: core/components/fill_array_kernels.hpp; common/unified/components/fill_array_kernels.cpp] */
+int gkob200_fill_array(void* stream, void* data, int64_t n, int elem_bytes, const void* value_host)
+{
+    if (n < 0 || !value_host || (n > 0 && !data)) return GKOB200_EINVAL;
+    uint64_t v = 0;
+    memcpy(&v, value_host, static_cast<size_t>(elem_bytes));
+    switch (elem_bytes) {
+    case 1: { auto* p = static_cast<uint8_t*>(data); const uint8_t x = static_cast<uint8_t>(v);
+              return launch_2d(as_stream(stream), n, 1, [=] __device__(int64_t i, int64_t) { p[i] = x; }); }
+    case 2: { auto* p = static_cast<uint16_t*>(data); const uint16_t x = static_cast<uint16_t>(v);
+              return launch_2d(as_stream(stream), n, 1, [=] __device__(int64_t i, int64_t) { p[i] = x; }); }
+    case 4: { auto* p = static_cast<uint32_t*>(data); const uint32_t x = static_cast<uint32_t>(v);
+              return launch_2d(as_stream(stream), n, 1, [=] __device__(int64_t i, int64_t) { p[i] = x; }); }
+    case 8: { auto* p = static_cast<uint64_t*>(data); const uint64_t x = v;
+              return launch_2d(as_stream(stream), n, 1, [=] __device__(int64_t i, int64_t) { p[i] = x; }); }
+    default: return GKOB200_EUNSUPPORTED;
+    }
+}
 
 int gkob200_version(void) { return 100; }
 int gkob200_sm_count(void) { return sm_count(); }
