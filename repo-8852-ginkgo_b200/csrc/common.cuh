@@ -194,6 +194,36 @@ __device__ __forceinline__ void grid_reduce(T (&v)[NV], T* partials, unsigned* t
     }
 }
 
+// Deferred variant for kernels whose CTAs must retire as fast as possible (the SpMV with a
+// fused dot holds 44 KB of shared memory per CTA: waiting for the ticket atomic's round trip
+// before exiting cost ~15 % of its throughput).  The kernel only stores one partial per CTA
+// — fire and forget — and `finish_partials` (one CTA, fixed order, deterministic) sums them.
+template <typename T>
+__device__ __forceinline__ void store_block_partial(T v, T* partials)
+{
+    __shared__ T red_p[32];
+    const T s = block_sum(v, red_p);
+    if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024) finish_partials(int64_t n, const T* __restrict__ partials, T* out, const int* skip)
+{
+    if (skip && *skip) return;
+    __shared__ T red[32];
+    T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
+    int64_t i = threadIdx.x;
+    for (; i + 3 * 1024 < n; i += 4 * 1024) {
+        a0 += partials[i];
+        a1 += partials[i + 1024];
+        a2 += partials[i + 2048];
+        a3 += partials[i + 3072];
+    }
+    for (; i < n; i += 1024) a0 += partials[i];
+    const T s = block_sum((a0 + a1) + (a2 + a3), red);
+    if (threadIdx.x == 0) out[0] = s;
+}
+
 // Scratch carried by every reducing kernel: ticket words followed by partials.
 // Layout of a reduction workspace (bytes): [0,1024) tickets, [1024, ...) partial sums.
 // GKOB200_REDUCE_WS_BYTES covers the largest grid the BLAS-1 kernels launch

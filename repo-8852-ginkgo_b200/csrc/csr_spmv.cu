@@ -75,6 +75,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                  : "memory");
 }
 
+// L2 prefetch of a byte range (16-byte aligned start, size a multiple of 16): the bulk
+// copies of a LATER tile then find their data in L2 instead of paying DRAM latency, which
+// raises the bytes in flight beyond what fits in shared memory.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 // ---------------------------------------------------------------------------
 // row-block kernel, single right-hand side
 // ---------------------------------------------------------------------------
@@ -147,14 +155,13 @@ __global__ void __launch_bounds__(kRowsPerCta)
 // the (at most 3) tail elements the 16-byte granularity leaves over.
 // Requires 16-byte aligned `values` / `col_idxs` base pointers.
 // ---------------------------------------------------------------------------
-template <typename V, typename I, bool Advanced, bool Fused>
+template <typename V, typename I, bool Advanced, bool Fused, int kBatch>
 __global__ void __launch_bounds__(kRowsPerCta)
     csr_spmv_rowblock_tma(int64_t n_rows, const I* __restrict__ row_ptrs, const I* __restrict__ col_idxs,
                           const V* __restrict__ values, const V* __restrict__ b, int64_t b_stride,
                           const V* __restrict__ alpha_p, const V* __restrict__ beta_p, V* __restrict__ c,
-                          int64_t c_stride, int cap, SpmvFusion<V> fu)
+                          int64_t c_stride, int cap, SpmvFusion<V> fu, int prefetch_tiles, int64_t nnz)
 {
-    if (Fused && fu.skip && *fu.skip) return;
     constexpr int VA = 16 / sizeof(V);  // elements per 16 bytes
     constexpr int IA = 16 / sizeof(I);
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -167,12 +174,21 @@ __global__ void __launch_bounds__(kRowsPerCta)
     const int64_t row0 = static_cast<int64_t>(blockIdx.x) * kRowsPerCta;
     const int nrow = static_cast<int>(min(static_cast<int64_t>(kRowsPerCta), n_rows - row0));
     if (tid == 0) mbar_init(&bar, 1);
-    // every thread reads its own two row pointers (coalesced, overlapping by one)
+    // Independent loads issued back to back so that their latencies overlap: the solver's
+    // "stopped" flag, this thread's two row pointers (coalesced, overlapping by one) and —
+    // for the fused dot — w[row], which is only needed in the epilogue.
+    int skip = 0;
+    V w_row = V(0);
+    if (Fused) {
+        if (fu.skip) skip = *fu.skip;
+        if (fu.out && tid < nrow) w_row = ldg(fu.w + row0 + tid);
+    }
     const I my_begin = row_ptrs[row0 + min(tid, nrow)];
     const I my_end = row_ptrs[row0 + min(tid + 1, nrow)];
     if (tid == 0) s_ptr[0] = my_begin;
     if (tid == nrow - 1) s_ptr[1] = my_end;
     __syncthreads();
+    if (Fused && skip) return;  // uniform: every thread read the same flag
     const I tile_begin = s_ptr[0];
     const I tile_end = s_ptr[1];
 
@@ -195,6 +211,13 @@ __global__ void __launch_bounds__(kRowsPerCta)
             mbar_expect_tx(&bar, vbytes + cbytes);
             if (vbytes) bulk_g2s(s_val, values + vb, vbytes, &bar);
             if (cbytes) bulk_g2s(s_col, col_idxs + cb, cbytes, &bar);
+            if (prefetch_tiles > 0) {
+                // stream-ahead hint: the same-sized window `prefetch_tiles` tiles further on
+                const int64_t ahead = static_cast<int64_t>(prefetch_tiles) * (tile_end - tile_begin);
+                const int64_t pv = vb + ahead, pc = cb + ahead;
+                if (vbytes && pv + (vf - vb) <= nnz) bulk_prefetch_l2(values + pv - (pv & (VA - 1)), vbytes);
+                if (cbytes && pc + (cf - cb) <= nnz) bulk_prefetch_l2(col_idxs + pc - (pc & (IA - 1)), cbytes);
+            }
         }
         // tails (< 16 bytes each) with plain loads
         {
@@ -213,7 +236,6 @@ __global__ void __launch_bounds__(kRowsPerCta)
         // batches of kBatch entries: all gathers of a batch are issued before the first
         // add, so a thread keeps kBatch L2/L1 requests in flight; the adds stay in
         // storage order (bit-identical to the oracle)
-        constexpr int kBatch = 9;
         for (I k = lo; k < hi; k += kBatch) {
             V v[kBatch], xv[kBatch];
 #pragma unroll
@@ -233,9 +255,8 @@ __global__ void __launch_bounds__(kRowsPerCta)
     }
     if (tid < nrow) c[(row0 + tid) * c_stride] = acc;
     if (Fused && fu.out) {
-        V t[1] = {tid < nrow ? acc * fu.w[row0 + tid] : V(0)};
-        V* out = fu.out;
-        grid_reduce<1>(t, ws_partials<V>(fu.ws), ws_ticket(fu.ws), [out](V(&tot)[1]) { out[0] = tot[0]; });
+        // one partial per CTA, summed by finish_partials right after this launch
+        store_block_partial(tid < nrow ? acc * w_row : V(0), ws_partials<V>(fu.ws));
     }
 }
 
@@ -524,6 +545,23 @@ inline int rowblock_variant()
     return v;
 }
 
+// tuning knobs of the row-block kernel (environment overrides exist only to A/B on the box)
+inline int env_int(const char* name, int dflt)
+{
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+inline int rowblock_batch()
+{
+    static int v = env_int("GKOB200_CSR_BATCH", 0);  // 0: from the mean row length
+    return v;
+}
+inline int rowblock_prefetch()
+{
+    static int v = env_int("GKOB200_CSR_PREFETCH", -1);  // -1: one resident wave
+    return v;
+}
+
 inline int rowblock_cap(int64_t max_block_nnz, size_t elem_bytes)
 {
     // shared-memory budget per CTA for the staged chunk: stays under the 48 KB
@@ -583,15 +621,37 @@ int csr_spmv_launch(cudaStream_t s, int64_t n_rows, int64_t n_cols, int64_t nnz,
         const bool aligned = (reinterpret_cast<uintptr_t>(values) % 16 == 0) &&
                              (reinterpret_cast<uintptr_t>(col_idxs) % 16 == 0);
         if (aligned && rowblock_variant() == 1) {
-#define GKOB200_RBT(ADV, FUSED)                                                                       \
-    csr_spmv_rowblock_tma<V, I, ADV, FUSED><<<grid, kRowsPerCta, smem, s>>>(                          \
-        n_rows, row_ptrs, col_idxs, values, b, b_stride, alpha, beta, c, c_stride, cap, fu)
-            if (adv && fused) GKOB200_RBT(true, true);
-            else if (adv) GKOB200_RBT(true, false);
-            else if (fused) GKOB200_RBT(false, true);
-            else GKOB200_RBT(false, false);
+            // stream-ahead distance: one wave of resident CTAs (shared-memory or thread bound)
+            int resident = static_cast<int>((227 * 1024) / (smem + 1024));
+            if (resident > 16) resident = 16;
+            if (resident < 1) resident = 1;
+            int pf = rowblock_prefetch();
+            if (pf < 0) pf = sm_count() * resident;
+            // gathers kept in flight per thread ~ the mean row length
+            int batch = rowblock_batch();
+            if (batch <= 0) {
+                const double mean = static_cast<double>(nnz) / static_cast<double>(n_rows);
+                batch = mean <= 5.5 ? 5 : mean <= 7.5 ? 7 : mean <= 10.5 ? 9 : 14;
+            }
+#define GKOB200_RBT(ADV, FUSED, BATCH)                                                                \
+    csr_spmv_rowblock_tma<V, I, ADV, FUSED, BATCH><<<grid, kRowsPerCta, smem, s>>>(                   \
+        n_rows, row_ptrs, col_idxs, values, b, b_stride, alpha, beta, c, c_stride, cap, fu, pf, nnz)
+#define GKOB200_RBT_B(BATCH)                                  \
+    if (adv && fused) GKOB200_RBT(true, true, BATCH);         \
+    else if (adv) GKOB200_RBT(true, false, BATCH);            \
+    else if (fused) GKOB200_RBT(false, true, BATCH);          \
+    else GKOB200_RBT(false, false, BATCH)
+            if (batch >= 14) { GKOB200_RBT_B(14); }
+            else if (batch >= 9) { GKOB200_RBT_B(9); }
+            else if (batch >= 7) { GKOB200_RBT_B(7); }
+            else { GKOB200_RBT_B(5); }
+#undef GKOB200_RBT_B
 #undef GKOB200_RBT
             GKOB200_CHECK_LAUNCH();
+            if (fused && fu.out) {
+                finish_partials<V><<<1, 1024, 0, s>>>(static_cast<int64_t>(grid), ws_partials<V>(fu.ws), fu.out, fu.skip);
+                GKOB200_CHECK_LAUNCH();
+            }
             return 0;
         }
         if (fused && fu.out && static_cast<int64_t>(grid) > fu.ws_blocks) return GKOB200_EWORKSPACE;

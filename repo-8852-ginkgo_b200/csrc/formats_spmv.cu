@@ -96,11 +96,7 @@ __global__ void __launch_bounds__(256)
         }
         c[r * c_stride] = acc;
     }
-    if (Fused && fu.out) {
-        V t[1] = {live ? acc * fu.w[r] : V(0)};
-        V* out = fu.out;
-        grid_reduce<1>(t, ws_partials<V>(fu.ws), ws_ticket(fu.ws), [out](V(&tot)[1]) { out[0] = tot[0]; });
-    }
+    if (Fused && fu.out) store_block_partial(live ? acc * fu.w[r] : V(0), ws_partials<V>(fu.ws));
 }
 
 // SpMM: warp = 32 rows x 32 RHS columns (lane = RHS column)
@@ -180,6 +176,10 @@ int strided_launch(cudaStream_t s, int64_t n_rows, Fmt fmt, const I* cols, const
     else GKOB200_ST(false, false);
 #undef GKOB200_ST
     GKOB200_CHECK_LAUNCH();
+    if (fused && fu.out) {
+        finish_partials<V><<<1, 1024, 0, s>>>(static_cast<int64_t>(grid), ws_partials<V>(fu.ws), fu.out, fu.skip);
+        GKOB200_CHECK_LAUNCH();
+    }
     return 0;
 }
 
