@@ -68,6 +68,10 @@ typedef struct gkob200_matrix {
     /* CSR_ROWS */
     const int32_t* row_list;
     int64_t n_listed;
+    /* SELL-P, optional host-side facts that enable the bulk-async kernel (0 = unknown:
+     * the thread-per-row kernel runs): max(slice_lengths) and slice_sets[n_slices] */
+    int64_t sellp_max_slice_len;
+    int64_t sellp_total_cols;
 } gkob200_matrix;
 
 /* c = A b  /  c = alpha A b + beta c  for any format of the descriptor

@@ -32,6 +32,7 @@ class Matrix(C.Structure):
         ("coo_nnz", i64), ("coo_row_idxs", vp), ("coo_col_idxs", vp), ("coo_values", vp),
         ("workspace", vp), ("workspace_bytes", sz),
         ("row_list", vp), ("n_listed", i64),
+        ("sellp_max_slice_len", i64), ("sellp_total_cols", i64),
     ]
 
 

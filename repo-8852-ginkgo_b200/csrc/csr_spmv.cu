@@ -28,6 +28,7 @@
 #include <cstdlib>
 
 #include "internal.h"
+#include "tma.cuh"
 
 namespace gkob200 {
 namespace {
@@ -38,50 +39,6 @@ constexpr int kRowsPerCta = 128;  // == blockDim.x of the row-block kernel
 // walks (stride = row length) conflict-free also for even row lengths.
 __device__ __forceinline__ int pad(int k) { return k + (k >> 5); }
 __host__ __device__ inline int padded_size(int cap) { return cap + (cap >> 5) + 1; }
-__host__ __device__ inline size_t align16(size_t b) { return (b + 15) & ~static_cast<size_t>(15); }
-
-// ---- bulk asynchronous copy (TMA engine, 1-D) + mbarrier, raw PTX ------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completion
-// is signalled on `bar` as transaction bytes.  SASS: UBLKCP.
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-// L2 prefetch of a byte range (16-byte aligned start, size a multiple of 16): the bulk
-// copies of a LATER tile then find their data in L2 instead of paying DRAM latency, which
-// raises the bytes in flight beyond what fits in shared memory.
-__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes)
-{
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
 
 // ---------------------------------------------------------------------------
 // row-block kernel, single right-hand side

@@ -86,12 +86,14 @@ __global__ void __launch_bounds__(256)
             }
 #pragma unroll
             for (int u = 0; u < kBatch; ++u)
-                xv[u] = col[u] != I(-1) ? ldg(b + static_cast<int64_t>(col[u]) * b_stride) : V(0);
+                // unconditional gather (padding reads x[0] and is discarded below): keeps the
+                // batch free of branches so that all loads are issued before the first add
+                xv[u] = ldg(b + static_cast<int64_t>(col[u] < I(0) ? I(0) : col[u]) * b_stride);
 #pragma unroll
             for (int u = 0; u < kBatch; ++u) {
-                if (col[u] != I(-1))
-                    acc = Advanced ? add_rn(acc, mul_rn(mul_rn(alpha, v[u]), xv[u]))
-                                   : add_rn(acc, mul_rn(v[u], xv[u]));
+                const V nxt = Advanced ? add_rn(acc, mul_rn(mul_rn(alpha, v[u]), xv[u]))
+                                       : add_rn(acc, mul_rn(v[u], xv[u]));
+                acc = col[u] != I(-1) ? nxt : acc;
             }
         }
         c[r * c_stride] = acc;
@@ -451,6 +453,11 @@ int ell_spmv_launch(cudaStream_t s, int64_t n_rows, int64_t stride, int64_t widt
         return GKOB200_EINVAL;
     if (n_rows == 0 || nrhs == 0) return 0;
     if (!c || (width > 0 && (!cols || !vals || !b))) return GKOB200_EINVAL;
+    if (nrhs == 1) {
+        const int rc = ell_spmv_tma_launch<V, I>(s, n_rows, stride, width, cols, vals, b, b_stride, alpha, beta, c,
+                                                 c_stride, fusion);
+        if (rc != 0) return rc == 1 ? 0 : rc;
+    }
     return strided_launch<V, I>(s, n_rows, EllFmt{stride, width}, cols, vals, b, b_stride, nrhs, alpha, beta, c,
                                 c_stride, fusion);
 }

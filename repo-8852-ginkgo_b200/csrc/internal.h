@@ -35,6 +35,16 @@ int sellp_spmv_launch(cudaStream_t s, int64_t n_rows, int64_t slice_size, const 
                       const uint64_t* slice_lengths, const I* cols, const V* vals, const V* b, int64_t b_stride,
                       int64_t nrhs, const V* alpha, const V* beta, V* c, int64_t c_stride,
                       const SpmvFusion<V>* fusion);
+// bulk-async (TMA) variants: return 1 when launched, 0 when the layout needs the fallback
+template <typename V, typename I>
+int sellp_spmv_tma_launch(cudaStream_t s, int64_t n_rows, int64_t slice_size, const uint64_t* slice_sets,
+                          int64_t max_slice_len, int64_t total_cols, const I* cols, const V* vals, const V* b,
+                          int64_t b_stride, const V* alpha, const V* beta, V* c, int64_t c_stride,
+                          const SpmvFusion<V>* fusion);
+template <typename V, typename I>
+int ell_spmv_tma_launch(cudaStream_t s, int64_t n_rows, int64_t stride, int64_t width, const I* cols, const V* vals,
+                        const V* b, int64_t b_stride, const V* alpha, const V* beta, V* c, int64_t c_stride,
+                        const SpmvFusion<V>* fusion);
 // accumulate == true: c += [alpha] A b (spmv2); false: c = A b / c = alpha A b + beta c
 template <typename V, typename I>
 int coo_spmv_launch(cudaStream_t s, int64_t n_rows, int64_t nnz, const I* rows, const I* cols, const V* vals,

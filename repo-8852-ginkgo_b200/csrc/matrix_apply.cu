@@ -76,6 +76,20 @@ int matrix_apply(cudaStream_t s, const gkob200_matrix& A, const V* b, int64_t b_
                                            static_cast<const V*>(A.ell_values), b, b_stride, nrhs, alpha, beta, c,
                                            c_stride, nrhs == 1 ? fp : nullptr);
     case GKOB200_FMT_SELLP:
+        if (nrhs == 1 && A.sellp_max_slice_len > 0) {
+            int rc = 0;
+            if (A.index_type == GKOB200_I32)
+                rc = sellp_spmv_tma_launch<V, int32_t>(s, A.n_rows, A.slice_size, A.slice_sets, A.sellp_max_slice_len,
+                                                       A.sellp_total_cols, static_cast<const int32_t*>(A.col_idxs),
+                                                       static_cast<const V*>(A.values), b, b_stride, alpha, beta, c,
+                                                       c_stride, fp);
+            else
+                rc = sellp_spmv_tma_launch<V, int64_t>(s, A.n_rows, A.slice_size, A.slice_sets, A.sellp_max_slice_len,
+                                                       A.sellp_total_cols, static_cast<const int64_t*>(A.col_idxs),
+                                                       static_cast<const V*>(A.values), b, b_stride, alpha, beta, c,
+                                                       c_stride, fp);
+            if (rc != 0) return rc == 1 ? 0 : rc;
+        }
         if (A.index_type == GKOB200_I32)
             return sellp_spmv_launch<V, int32_t>(s, A.n_rows, A.slice_size, A.slice_sets, A.slice_lengths,
                                                  static_cast<const int32_t*>(A.col_idxs),

@@ -1,0 +1,287 @@
+// strided_tma.cu — SELL-P and ELL SpMV with bulk-async (TMA) staging: the same design as
+// the CSR row-block kernel (csr_spmv.cu).  A CTA of 128 threads owns 128 consecutive rows;
+//  * SELL-P: those rows are whole slices (slice_size 32 / 64 / 128), each slice one
+//    contiguous, 16-byte aligned block  [slice_sets[s]*slice_size, slice_sets[s+1]*slice_size)
+//    -> one bulk copy per slice and array;
+//  * ELL: column i of the 128 rows is contiguous (column-major storage) -> one bulk copy
+//    per stored column and array (needs stride*sizeof % 16 == 0).
+// Thread t then walks row t out of shared memory with stride-1 (conflict-free) accesses,
+// gathers kept in flight in batches, sums in storage order with a rounded product and a
+// rounded sum (bit-identical to reference/matrix/{sellp,ell}_kernels.cpp), skipping the
+// padding entries (col == -1).  An L2 prefetch of the window one resident wave ahead keeps
+// more bytes in flight than shared memory alone can hold.
+// Falls back to the thread-per-row kernel of formats_spmv.cu when the layout does not allow
+// bulk copies (odd slice sizes, unaligned strides, tiles larger than shared memory).
+#include "internal.h"
+#include "tma.cuh"
+
+namespace gkob200 {
+namespace {
+
+constexpr int kRows = 128;
+
+template <typename V, typename I, bool Advanced, bool Fused, int kBatch>
+__global__ void __launch_bounds__(kRows)
+    sellp_spmv_tma(int64_t n_rows, int slice_size, const uint64_t* __restrict__ slice_sets,
+                   const I* __restrict__ cols, const V* __restrict__ vals, const V* __restrict__ b, int64_t b_stride,
+                   const V* __restrict__ alpha_p, const V* __restrict__ beta_p, V* __restrict__ c, int64_t c_stride,
+                   int cap, SpmvFusion<V> fu, int prefetch_tiles, int64_t total_elems)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    V* s_val = reinterpret_cast<V*>(smem_raw);
+    I* s_col = reinterpret_cast<I*>(smem_raw + align16(static_cast<size_t>(cap) * sizeof(V)));
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ int64_t s_set[6];  // slice_sets of the (<= 4) slices of this CTA, +1
+
+    const int tid = threadIdx.x;
+    const int spc = kRows / slice_size;  // slices per CTA
+    const int64_t slice0 = static_cast<int64_t>(blockIdx.x) * spc;
+    const int64_t n_slices = (n_rows + slice_size - 1) / slice_size;
+    const int ns = static_cast<int>(min(static_cast<int64_t>(spc), n_slices - slice0));
+    const int64_t row = slice0 * slice_size + tid;
+    int skip = 0;
+    V w_row = V(0);
+    if (Fused) {
+        if (fu.skip) skip = *fu.skip;
+        if (fu.out && row < n_rows) w_row = ldg(fu.w + row);
+    }
+    if (tid <= ns) s_set[tid] = static_cast<int64_t>(slice_sets[slice0 + tid]);
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (Fused && skip) return;
+    const int64_t begin = s_set[0] * slice_size, end = s_set[ns] * slice_size;  // element range of the tile
+    if (tid == 0) {
+        const unsigned n_el = static_cast<unsigned>(end - begin);
+        mbar_expect_tx(&bar, n_el * static_cast<unsigned>(sizeof(V) + sizeof(I)));
+        if (n_el) {
+            bulk_g2s(s_val, vals + begin, n_el * sizeof(V), &bar);
+            bulk_g2s(s_col, cols + begin, n_el * sizeof(I), &bar);
+            if (prefetch_tiles > 0) {
+                const int64_t ahead = begin + static_cast<int64_t>(prefetch_tiles) * n_el;
+                if (ahead + n_el <= total_elems) {
+                    bulk_prefetch_l2(vals + ahead, n_el * sizeof(V));
+                    bulk_prefetch_l2(cols + ahead, n_el * sizeof(I));
+                }
+            }
+        }
+    }
+    const int sl = tid / slice_size, local = tid - sl * slice_size;
+    const bool live = row < n_rows && sl < ns;
+    V alpha = V(1), acc = V(0);
+    if (Advanced) {
+        alpha = *alpha_p;
+        if (live) acc = mul_rn(c[row * c_stride], *beta_p);
+    }
+    mbar_wait(&bar, 0);
+    if (live) {
+        const int64_t base = (s_set[sl] - s_set[0]) * slice_size + local;
+        const int len = static_cast<int>(s_set[sl + 1] - s_set[sl]);
+        for (int i = 0; i < len; i += kBatch) {
+            V v[kBatch], xv[kBatch];
+            unsigned valid = 0;
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                // same shape as the CSR row-block kernel: value, column and gather of one entry
+                // together, all kBatch gathers issued before the first add
+                const bool in = i + u < len;
+                const I col = in ? s_col[base + static_cast<int64_t>(i + u) * slice_size] : I(-1);
+                v[u] = in ? s_val[base + static_cast<int64_t>(i + u) * slice_size] : V(0);
+                const bool ok = col != I(-1);
+                xv[u] = ok ? ldg(b + static_cast<int64_t>(col) * b_stride) : V(0);
+                valid |= static_cast<unsigned>(ok) << u;
+            }
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                if ((valid >> u) & 1u)
+                    acc = Advanced ? add_rn(acc, mul_rn(mul_rn(alpha, v[u]), xv[u])) : add_rn(acc, mul_rn(v[u], xv[u]));
+            }
+        }
+        c[row * c_stride] = acc;
+    }
+    if (Fused && fu.out) store_block_partial(live ? acc * w_row : V(0), ws_partials<V>(fu.ws));
+}
+
+template <typename V, typename I, bool Advanced, bool Fused, int kBatch>
+__global__ void __launch_bounds__(kRows)
+    ell_spmv_tma(int64_t n_rows, int64_t stride, int width, const I* __restrict__ cols, const V* __restrict__ vals,
+                 const V* __restrict__ b, int64_t b_stride, const V* __restrict__ alpha_p, const V* __restrict__ beta_p,
+                 V* __restrict__ c, int64_t c_stride, SpmvFusion<V> fu, int prefetch_tiles)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    V* s_val = reinterpret_cast<V*>(smem_raw);
+    I* s_col = reinterpret_cast<I*>(smem_raw + align16(static_cast<size_t>(width) * kRows * sizeof(V)));
+    __shared__ __align__(8) uint64_t bar;
+
+    const int tid = threadIdx.x;
+    const int64_t row0 = static_cast<int64_t>(blockIdx.x) * kRows;
+    const int nrow = static_cast<int>(min(static_cast<int64_t>(kRows), n_rows - row0));
+    const int64_t row = row0 + tid;
+    int skip = 0;
+    V w_row = V(0);
+    if (Fused) {
+        if (fu.skip) skip = *fu.skip;
+        if (fu.out && tid < nrow) w_row = ldg(fu.w + row);
+    }
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (Fused && skip) return;
+    // rows of the last, partial tile: round the copy length up to 16 bytes (stays inside the
+    // column because stride >= n_rows rounded to the same granularity is checked on the host)
+    constexpr int VA = 16 / sizeof(V), IA = 16 / sizeof(I);
+    const unsigned nv = static_cast<unsigned>((nrow + VA - 1) / VA * VA), ni = static_cast<unsigned>((nrow + IA - 1) / IA * IA);
+    if (tid == 0) {
+        mbar_expect_tx(&bar, static_cast<unsigned>(width) * (nv * sizeof(V) + ni * sizeof(I)));
+        for (int i = 0; i < width; ++i) {
+            bulk_g2s(s_val + i * kRows, vals + row0 + i * stride, nv * sizeof(V), &bar);
+            bulk_g2s(s_col + i * kRows, cols + row0 + i * stride, ni * sizeof(I), &bar);
+        }
+        if (prefetch_tiles > 0) {
+            const int64_t ahead = row0 + static_cast<int64_t>(prefetch_tiles) * kRows;
+            if (ahead + kRows <= n_rows)
+                for (int i = 0; i < width; ++i) {
+                    bulk_prefetch_l2(vals + ahead + i * stride, kRows * sizeof(V));
+                    bulk_prefetch_l2(cols + ahead + i * stride, kRows * sizeof(I));
+                }
+        }
+    }
+    const bool live = tid < nrow;
+    V alpha = V(1), acc = V(0);
+    if (Advanced) {
+        alpha = *alpha_p;
+        if (live) acc = mul_rn(c[row * c_stride], *beta_p);
+    }
+    mbar_wait(&bar, 0);
+    if (live) {
+        for (int i = 0; i < width; i += kBatch) {
+            V v[kBatch], xv[kBatch];
+            unsigned valid = 0;
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const bool in = i + u < width;
+                const I col = in ? s_col[(i + u) * kRows + tid] : I(-1);
+                v[u] = in ? s_val[(i + u) * kRows + tid] : V(0);
+                const bool ok = col != I(-1);
+                xv[u] = ok ? ldg(b + static_cast<int64_t>(col) * b_stride) : V(0);
+                valid |= static_cast<unsigned>(ok) << u;
+            }
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                if ((valid >> u) & 1u)
+                    acc = Advanced ? add_rn(acc, mul_rn(mul_rn(alpha, v[u]), xv[u])) : add_rn(acc, mul_rn(v[u], xv[u]));
+            }
+        }
+        c[row * c_stride] = acc;
+    }
+    if (Fused && fu.out) store_block_partial(live ? acc * w_row : V(0), ws_partials<V>(fu.ws));
+}
+
+inline int resident_ctas(size_t smem)
+{
+    int r = static_cast<int>((227 * 1024) / (smem + 1024));
+    return r > 16 ? 16 : (r < 1 ? 1 : r);
+}
+
+constexpr size_t kMaxTileBytes = 100 * 1024;  // beyond this the thread-per-row kernel takes over
+
+}  // namespace
+
+// returns 1 if the launch was done, 0 if the caller must fall back, <0 / >0 on error
+template <typename V, typename I>
+int sellp_spmv_tma_launch(cudaStream_t s, int64_t n_rows, int64_t slice_size, const uint64_t* slice_sets,
+                          int64_t max_slice_len, int64_t total_cols, const I* cols, const V* vals, const V* b,
+                          int64_t b_stride, const V* alpha, const V* beta, V* c, int64_t c_stride,
+                          const SpmvFusion<V>* fusion)
+{
+    if (slice_size != 32 && slice_size != 64 && slice_size != 128) return 0;
+    if (max_slice_len <= 0 || reinterpret_cast<uintptr_t>(vals) % 16 || reinterpret_cast<uintptr_t>(cols) % 16) return 0;
+    const int cap = static_cast<int>(max_slice_len * kRows);
+    const size_t smem = align16(static_cast<size_t>(cap) * sizeof(V)) + align16(static_cast<size_t>(cap) * sizeof(I));
+    if (smem > kMaxTileBytes) return 0;
+    const int spc = kRows / static_cast<int>(slice_size);
+    const int64_t n_slices = ceildiv(n_rows, slice_size);
+    const unsigned grid = static_cast<unsigned>(ceildiv(n_slices, spc));
+    SpmvFusion<V> fu;
+    if (fusion) fu = *fusion;
+    const bool fused = fusion != nullptr, adv = alpha != nullptr;
+    if (fused && fu.out && static_cast<int64_t>(grid) > fu.ws_blocks) return GKOB200_EWORKSPACE;
+    const int pf = sm_count() * resident_ctas(smem);
+    const int64_t total = total_cols * slice_size;
+#define GKOB200_SP(ADV, FUSED, BATCH)                                                                             \
+    {                                                                                                             \
+        auto kern = sellp_spmv_tma<V, I, ADV, FUSED, BATCH>;                                                       \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTileBytes); \
+        kern<<<grid, kRows, smem, s>>>(n_rows, static_cast<int>(slice_size), slice_sets, cols, vals, b, b_stride,  \
+                                       alpha, beta, c, c_stride, cap, fu, pf, total);                              \
+    }
+    const bool wide = max_slice_len > 10;
+    if (wide) {
+        if (adv && fused) GKOB200_SP(true, true, 14) else if (adv) GKOB200_SP(true, false, 14)
+        else if (fused) GKOB200_SP(false, true, 14) else GKOB200_SP(false, false, 14)
+    } else {
+        if (adv && fused) GKOB200_SP(true, true, 7) else if (adv) GKOB200_SP(true, false, 7)
+        else if (fused) GKOB200_SP(false, true, 7) else GKOB200_SP(false, false, 7)
+    }
+#undef GKOB200_SP
+    GKOB200_CHECK_LAUNCH();
+    if (fused && fu.out) {
+        finish_partials<V><<<1, 1024, 0, s>>>(static_cast<int64_t>(grid), ws_partials<V>(fu.ws), fu.out, fu.skip);
+        GKOB200_CHECK_LAUNCH();
+    }
+    return 1;
+}
+
+template <typename V, typename I>
+int ell_spmv_tma_launch(cudaStream_t s, int64_t n_rows, int64_t stride, int64_t width, const I* cols, const V* vals,
+                        const V* b, int64_t b_stride, const V* alpha, const V* beta, V* c, int64_t c_stride,
+                        const SpmvFusion<V>* fusion)
+{
+    if (width <= 0 || width > 64) return 0;
+    if ((stride * sizeof(V)) % 16 || (stride * sizeof(I)) % 16 || reinterpret_cast<uintptr_t>(vals) % 16 ||
+        reinterpret_cast<uintptr_t>(cols) % 16)
+        return 0;
+    // the padded copy of the last tile must stay inside a column
+    if (ceildiv(n_rows, 4) * 4 > stride) return 0;
+    const size_t smem = align16(static_cast<size_t>(width) * kRows * sizeof(V)) + align16(static_cast<size_t>(width) * kRows * sizeof(I));
+    if (smem > kMaxTileBytes) return 0;
+    const unsigned grid = static_cast<unsigned>(ceildiv(n_rows, kRows));
+    SpmvFusion<V> fu;
+    if (fusion) fu = *fusion;
+    const bool fused = fusion != nullptr, adv = alpha != nullptr;
+    if (fused && fu.out && static_cast<int64_t>(grid) > fu.ws_blocks) return GKOB200_EWORKSPACE;
+    const int pf = sm_count() * resident_ctas(smem);
+#define GKOB200_EL(ADV, FUSED, BATCH)                                                                             \
+    {                                                                                                             \
+        auto kern = ell_spmv_tma<V, I, ADV, FUSED, BATCH>;                                                         \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTileBytes); \
+        kern<<<grid, kRows, smem, s>>>(n_rows, stride, static_cast<int>(width), cols, vals, b, b_stride, alpha,    \
+                                       beta, c, c_stride, fu, pf);                                                 \
+    }
+    if (width > 10) {
+        if (adv && fused) GKOB200_EL(true, true, 14) else if (adv) GKOB200_EL(true, false, 14)
+        else if (fused) GKOB200_EL(false, true, 14) else GKOB200_EL(false, false, 14)
+    } else {
+        if (adv && fused) GKOB200_EL(true, true, 7) else if (adv) GKOB200_EL(true, false, 7)
+        else if (fused) GKOB200_EL(false, true, 7) else GKOB200_EL(false, false, 7)
+    }
+#undef GKOB200_EL
+    GKOB200_CHECK_LAUNCH();
+    if (fused && fu.out) {
+        finish_partials<V><<<1, 1024, 0, s>>>(static_cast<int64_t>(grid), ws_partials<V>(fu.ws), fu.out, fu.skip);
+        GKOB200_CHECK_LAUNCH();
+    }
+    return 1;
+}
+
+#define GKOB200_INST(V, I)                                                                                         \
+    template int sellp_spmv_tma_launch<V, I>(cudaStream_t, int64_t, int64_t, const uint64_t*, int64_t, int64_t,    \
+                                             const I*, const V*, const V*, int64_t, const V*, const V*, V*,        \
+                                             int64_t, const SpmvFusion<V>*);                                       \
+    template int ell_spmv_tma_launch<V, I>(cudaStream_t, int64_t, int64_t, int64_t, const I*, const V*, const V*,  \
+                                           int64_t, const V*, const V*, V*, int64_t, const SpmvFusion<V>*);
+GKOB200_INST(double, int32_t)
+GKOB200_INST(float, int32_t)
+GKOB200_INST(double, int64_t)
+GKOB200_INST(float, int64_t)
+#undef GKOB200_INST
+
+}  // namespace gkob200

@@ -344,6 +344,9 @@ class Sellp(_SparseBase):
         self.slice_size, self.stride_factor = int(slice_size), int(stride_factor)
         self.slice_sets, self.slice_lengths, self.col_idxs, self.values = slice_sets, slice_lengths, col_idxs, values
         self.V, self.I = vname(values.dtype), iname(col_idxs.dtype)
+        # host-side facts the bulk-async kernel sizes its shared memory with
+        self.max_slice_len = int(slice_lengths.max().item()) if slice_lengths.numel() else 0
+        self.total_cols = int(slice_sets[-1].item()) if slice_sets.numel() else 0
 
     def descriptor(self):
         d = _abi.Matrix()
@@ -356,6 +359,7 @@ class Sellp(_SparseBase):
         d.slice_size, d.stride_factor = self.slice_size, self.stride_factor
         d.n_slices = self.slice_lengths.numel()
         d.slice_sets, d.slice_lengths = self.slice_sets.data_ptr(), self.slice_lengths.data_ptr()
+        d.sellp_max_slice_len, d.sellp_total_cols = self.max_slice_len, self.total_cols
         return d
 
     def kernel(self):
