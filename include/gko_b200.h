@@ -70,7 +70,11 @@ enum gkob200_csr_strategy {
                                    memory, one thread per row, oracle summation order
                                    (bit-identical to the reference executor)          */
     GKOB200_CSR_MERGE_PATH = 1, /* load-balanced merge-path kernel (skewed rows)      */
-    GKOB200_CSR_AUTO = 2        /* = pick_strategy() when stats are given, else MERGE  */
+    GKOB200_CSR_AUTO = 2,       /* = pick_strategy() when stats are given, else MERGE  */
+    GKOB200_CSR_MERGE_PATH_PLANNED = 3 /* merge-path with the per-tile split rows precomputed in
+                                          `workspace` by gkob200_csr_merge_plan_* (the counterpart of
+                                          the srow array Csr::make_srow() fills for load_balance,
+                                          include/ginkgo/core/matrix/csr.hpp:421-511)           */
 };
 
 /* Row-length statistics of a CSR matrix (device kernel, result on device):
@@ -94,8 +98,14 @@ GKOB200_DECL_CSR_SPMV(f64, double, i32, int32_t)
 GKOB200_DECL_CSR_SPMV(f32, float, i32, int32_t)
 GKOB200_DECL_CSR_SPMV(f64, double, i64, int64_t)
 GKOB200_DECL_CSR_SPMV(f32, float, i64, int64_t)
-/* Workspace the merge-path kernel needs for its per-tile carries (bytes). */
+/* Workspace the merge-path kernel needs for its per-tile carries and plan (bytes). */
 size_t gkob200_csr_spmv_workspace_bytes(int64_t n_rows, int64_t nnz, int64_t nrhs, int value_bytes);
+/* Once per matrix: store the merge-path split row of every tile in `workspace`
+ * (sized with value_bytes = 8); enables strategy GKOB200_CSR_MERGE_PATH_PLANNED. */
+int gkob200_csr_merge_plan_i32(void* stream, int64_t n_rows, int64_t nnz, const int32_t* row_ptrs, void* workspace,
+                               size_t workspace_bytes);
+int gkob200_csr_merge_plan_i64(void* stream, int64_t n_rows, int64_t nnz, const int64_t* row_ptrs, void* workspace,
+                               size_t workspace_bytes);
 
 /* ------------------------------------------------------------------------- *
  * ELL / SELL-P / COO SpMV and SpMM

@@ -11,7 +11,7 @@ VT = {"f64": f64, "f32": f32}
 EINVAL, EUNSUPPORTED, EWORKSPACE = -1, -2, -3
 REDUCE_WS_BYTES = 1024 + (148 * 16 + 256) * 8 * 8
 
-CSR_CLASSICAL, CSR_MERGE_PATH, CSR_AUTO = 0, 1, 2
+CSR_CLASSICAL, CSR_MERGE_PATH, CSR_AUTO, CSR_MERGE_PATH_PLANNED = 0, 1, 2, 3
 F64, F32 = 0, 1
 I32, I64 = 0, 1
 FMT_CSR, FMT_ELL, FMT_SELLP, FMT_COO, FMT_HYBRID, FMT_CSR_ROWS = range(6)
@@ -64,6 +64,8 @@ def declare(lib):
     for I in ("i32", "i64"):
         d(f"gkob200_csr_row_stats_{I}", [vp, i64, vp, vp])
     d("gkob200_csr_pick_strategy", [i64, i64, i64, i64])
+    for I in ("i32", "i64"):
+        d(f"gkob200_csr_merge_plan_{I}", [vp, i64, i64, vp, vp, sz])
     d("gkob200_csr_spmv_workspace_bytes", [i64, i64, i64, C.c_int], sz)
     for V, T in VT.items():
         for I in ("i32", "i64"):

@@ -289,8 +289,8 @@ __global__ void __launch_bounds__(kRowsPerCta)
 // ---------------------------------------------------------------------------
 // merge-path kernel (single right-hand side)
 // ---------------------------------------------------------------------------
-constexpr int kMpThreads = 128;
-constexpr int kMpItems = 7;                            // merge items per thread (odd: conflict-free)
+constexpr int kMpThreads = 256;
+constexpr int kMpItems = 9;                            // merge items per thread (odd: conflict-free)
 constexpr int kMpTile = kMpThreads * kMpItems;         // merge items per CTA
 
 // Merge-path diagonal search: how many of the first `diag` merge items are row
@@ -317,7 +317,8 @@ __global__ void __launch_bounds__(kMpThreads)
     csr_spmv_merge(int64_t n_rows, int64_t nnz, const I* __restrict__ row_ptrs, const I* __restrict__ col_idxs,
                    const V* __restrict__ values, const V* __restrict__ b, int64_t b_stride,
                    const V* __restrict__ alpha_p, const V* __restrict__ beta_p, V* __restrict__ c,
-                   int64_t c_stride, int64_t* __restrict__ carry_row, V* __restrict__ carry_val)
+                   int64_t c_stride, int64_t* __restrict__ carry_row, V* __restrict__ carry_val,
+                   const int64_t* __restrict__ plan)
 {
     __shared__ V s_prod[kMpTile + 1];
     __shared__ I s_rowend[kMpTile + 1];
@@ -332,7 +333,10 @@ __global__ void __launch_bounds__(kMpThreads)
     const I* row_end = row_ptrs + 1;
     if (tid < 2) {
         const int64_t d = tid == 0 ? diag0 : diag1;
-        const int64_t r = merge_path_search<I>(d, row_end, n_rows, nnz);
+        // planned: the tile's split point was computed once per matrix (gkob200_csr_merge_plan_*),
+        // otherwise two binary searches over row_ptrs per CTA and per call (24 dependent loads
+        // at 10^7 rows — most of the kernel's time on skewed matrices)
+        const int64_t r = plan ? plan[blockIdx.x + tid] : merge_path_search<I>(d, row_end, n_rows, nnz);
         s_range[tid * 2] = r;
         s_range[tid * 2 + 1] = d - r;
     }
@@ -344,12 +348,29 @@ __global__ void __launch_bounds__(kMpThreads)
     V alpha = V(1);
     if (Advanced) alpha = *alpha_p;
 
-    // coalesced staging: products and row-end offsets (relative to k_begin)
-    for (int k = tid; k < n_tile_nnz; k += kMpThreads) {
-        const V v = values[k_begin + k];
-        const I col = col_idxs[k_begin + k];
-        const V xv = ldg(b + static_cast<int64_t>(col) * b_stride);
-        s_prod[k] = Advanced ? mul_rn(mul_rn(alpha, v), xv) : mul_rn(v, xv);
+    // coalesced staging: products and row-end offsets (relative to k_begin).  Every thread
+    // first issues all its (col, val) loads, then all its gathers, then forms the products:
+    // up to kMpItems independent requests in flight per thread (the gathers of a skewed
+    // matrix are random 32-byte sectors — latency, not bandwidth, is what has to be hidden).
+    // Streams are marked evict_first, the gathered vector evict_last (see tma.cuh).
+    {
+        const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+        V v[kMpItems], xv[kMpItems];
+        I col[kMpItems];
+#pragma unroll
+        for (int u = 0; u < kMpItems; ++u) {
+            const int k = tid + u * kMpThreads;
+            const bool in = k < n_tile_nnz;
+            col[u] = in ? ld_hint(col_idxs + k_begin + k, pol_stream) : I(0);
+            v[u] = in ? ld_hint(values + k_begin + k, pol_stream) : V(0);
+        }
+#pragma unroll
+        for (int u = 0; u < kMpItems; ++u) xv[u] = ld_hint(b + static_cast<int64_t>(col[u]) * b_stride, pol_keep);
+#pragma unroll
+        for (int u = 0; u < kMpItems; ++u) {
+            const int k = tid + u * kMpThreads;
+            if (k < n_tile_nnz) s_prod[k] = Advanced ? mul_rn(mul_rn(alpha, v[u]), xv[u]) : mul_rn(v[u], xv[u]);
+        }
     }
     for (int r = tid; r < n_tile_rows; r += kMpThreads) {
         s_rowend[r] = static_cast<I>(static_cast<int64_t>(row_end[r_begin + r]) - k_begin);
@@ -426,6 +447,18 @@ __global__ void __launch_bounds__(kMpThreads)
     }
     // (the last thread always ends with open row == n_tile_rows, so the leader of
     // that run has written this tile's carry)
+}
+
+// split row of every tile diagonal, computed once per matrix
+template <typename I>
+__global__ void csr_merge_plan(int64_t n_tiles, int64_t n_rows, int64_t nnz, const I* __restrict__ row_ptrs,
+                               int64_t* __restrict__ plan)
+{
+    const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (t > n_tiles) return;
+    const int64_t total = n_rows + nnz;
+    const int64_t d = min(t * kMpTile, total);
+    plan[t] = merge_path_search<I>(d, row_ptrs + 1, n_rows, nnz);
 }
 
 // Fix-up: tile carries belonging to the same row are consecutive; the first tile
@@ -623,21 +656,22 @@ int csr_spmv_launch(cudaStream_t s, int64_t n_rows, int64_t n_cols, int64_t nnz,
         GKOB200_CHECK_LAUNCH();
         return 0;
     }
-    if (strategy != GKOB200_CSR_MERGE_PATH) return GKOB200_EINVAL;
+    if (strategy != GKOB200_CSR_MERGE_PATH && strategy != GKOB200_CSR_MERGE_PATH_PLANNED) return GKOB200_EINVAL;
     if (fused && (fu.out || fu.skip)) return GKOB200_EUNSUPPORTED;
     const int64_t n_tiles = ceildiv(n_rows + nnz, kMpTile);
     const size_t need = gkob200_csr_spmv_workspace_bytes(n_rows, nnz, nrhs, sizeof(V));
     if (!workspace || workspace_bytes < need) return GKOB200_EWORKSPACE;
     int64_t* carry_row = reinterpret_cast<int64_t*>(workspace);
-    V* carry_val = reinterpret_cast<V*>(carry_row + n_tiles);
+    const int64_t* plan = strategy == GKOB200_CSR_MERGE_PATH_PLANNED ? carry_row + n_tiles + 1 : nullptr;
+    V* carry_val = reinterpret_cast<V*>(carry_row + 2 * (n_tiles + 1) + 1);
     if (adv)
         csr_spmv_merge<V, I, true><<<static_cast<unsigned>(n_tiles), kMpThreads, 0, s>>>(
             n_rows, nnz, row_ptrs, col_idxs, values, b, b_stride, alpha, beta, c, c_stride, carry_row,
-            carry_val);
+            carry_val, plan);
     else
         csr_spmv_merge<V, I, false><<<static_cast<unsigned>(n_tiles), kMpThreads, 0, s>>>(
             n_rows, nnz, row_ptrs, col_idxs, values, b, b_stride, alpha, beta, c, c_stride, carry_row,
-            carry_val);
+            carry_val, plan);
     GKOB200_CHECK_LAUNCH();
     csr_spmv_merge_fixup<V><<<static_cast<unsigned>(ceildiv(n_tiles, 256)), 256, 0, s>>>(
         static_cast<int>(n_tiles), carry_row, carry_val, n_rows, c, c_stride);
@@ -659,13 +693,29 @@ GKOB200_INST(float, int64_t)
 
 using namespace gkob200;
 
+template <typename I>
+static int merge_plan_impl(void* stream, int64_t n_rows, int64_t nnz, const I* row_ptrs, void* workspace,
+                           size_t workspace_bytes)
+{
+    if (n_rows < 0 || nnz < 0) return GKOB200_EINVAL;
+    if (n_rows == 0) return 0;
+    if (!row_ptrs) return GKOB200_EINVAL;
+    if (!workspace || workspace_bytes < gkob200_csr_spmv_workspace_bytes(n_rows, nnz, 1, 8)) return GKOB200_EWORKSPACE;
+    const int64_t n_tiles = ceildiv(n_rows + nnz, kMpTile);
+    int64_t* plan = reinterpret_cast<int64_t*>(workspace) + n_tiles + 1;
+    csr_merge_plan<I><<<static_cast<unsigned>(ceildiv(n_tiles + 1, 256)), 256, 0, as_stream(stream)>>>(n_tiles, n_rows, nnz,
+                                                                                                   row_ptrs, plan);
+    GKOB200_CHECK_LAUNCH();
+    return 0;
+}
 extern "C" {
 
 size_t gkob200_csr_spmv_workspace_bytes(int64_t n_rows, int64_t nnz, int64_t nrhs, int value_bytes)
 {
     (void)nrhs;
-    const int64_t n_tiles = ceildiv(n_rows + nnz, kMpTile) + 1;
-    return static_cast<size_t>(n_tiles) * (sizeof(int64_t) + static_cast<size_t>(value_bytes)) + 64;
+    // [carry_row: n_tiles+1][plan (tile split rows): n_tiles+2][carry_val: n_tiles+1]
+    const int64_t n_tiles = ceildiv(n_rows + nnz, kMpTile) + 2;
+    return static_cast<size_t>(n_tiles) * (2 * sizeof(int64_t) + static_cast<size_t>(value_bytes)) + 64;
 }
 
 int gkob200_csr_pick_strategy(int64_t n_rows, int64_t nnz, int64_t max_row_nnz, int64_t max_block_nnz)
@@ -682,6 +732,15 @@ int gkob200_csr_pick_strategy(int64_t n_rows, int64_t nnz, int64_t max_row_nnz, 
     if (max_row_nnz > 0 && static_cast<double>(max_row_nnz) > 8.0 * mean_row + 256.0)
         return GKOB200_CSR_MERGE_PATH;
     return GKOB200_CSR_CLASSICAL;
+}
+
+int gkob200_csr_merge_plan_i32(void* stream, int64_t n_rows, int64_t nnz, const int32_t* row_ptrs, void* ws, size_t wsb)
+{
+    return merge_plan_impl<int32_t>(stream, n_rows, nnz, row_ptrs, ws, wsb);
+}
+int gkob200_csr_merge_plan_i64(void* stream, int64_t n_rows, int64_t nnz, const int64_t* row_ptrs, void* ws, size_t wsb)
+{
+    return merge_plan_impl<int64_t>(stream, n_rows, nnz, row_ptrs, ws, wsb);
 }
 
 int gkob200_csr_row_stats_i32(void* stream, int64_t n_rows, const int32_t* row_ptrs, int64_t* stats)

@@ -41,7 +41,7 @@ int matrix_apply(cudaStream_t s, const gkob200_matrix& A, const V* b, int64_t b_
             strategy = A.csr_max_block_nnz > 0
                            ? gkob200_csr_pick_strategy(A.n_rows, A.nnz, -1, A.csr_max_block_nnz)
                            : GKOB200_CSR_MERGE_PATH;
-        if (strategy == GKOB200_CSR_MERGE_PATH && fp) {
+        if ((strategy == GKOB200_CSR_MERGE_PATH || strategy == GKOB200_CSR_MERGE_PATH_PLANNED) && fp) {
             // the merge-path kernel has no skip/dot fusion; its extra work after the
             // solver stopped only touches solver workspace
             fp = nullptr;

@@ -53,5 +53,46 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes
 }
 
 
+// ---- L2 residency hints ------------------------------------------------------------
+// B200's 126 MB L2 can hold the whole gathered vector x of a 10^7-row problem (80 MB) if
+// the streamed matrix arrays do not evict it: the streams are loaded with an evict_first
+// policy, the gathers with evict_last.
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ double ld_hint(const double* a, uint64_t pol)
+{
+    double v;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(a), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ float ld_hint(const float* a, uint64_t pol)
+{
+    float v;
+    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(a), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ int32_t ld_hint(const int32_t* a, uint64_t pol)
+{
+    int32_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ int64_t ld_hint(const int64_t* a, uint64_t pol)
+{
+    int64_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.s64 %0, [%1], %2;" : "=l"(v) : "l"(a), "l"(pol));
+    return v;
+}
+
 }  // namespace
 }  // namespace gkob200

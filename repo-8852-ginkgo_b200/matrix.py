@@ -239,9 +239,14 @@ class Csr(_SparseBase):
                                             self.values.data_ptr())
         d.csr_max_block_nnz = self.max_block_nnz
         if d.csr_strategy == _abi.CSR_MERGE_PATH:
-            nbytes = lib.gkob200_csr_spmv_workspace_bytes(self.size[0], self.nnz, 1, self.values.element_size())
+            # plan once per matrix (the role of the srow array of Csr::make_srow())
+            nbytes = lib.gkob200_csr_spmv_workspace_bytes(self.size[0], self.nnz, 1, 8)
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.exec.device)
             d.workspace, d.workspace_bytes = self._ws.data_ptr(), nbytes
+            check(getattr(lib, f"gkob200_csr_merge_plan_{self.I}")(current_stream(), self.size[0], self.nnz,
+                                                                   ptr(self.row_ptrs), ptr(self._ws), nbytes),
+                  "csr::merge_plan")
+            d.csr_strategy = _abi.CSR_MERGE_PATH_PLANNED
         self._desc = d
         return d
 
