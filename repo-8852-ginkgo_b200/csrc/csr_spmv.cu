@@ -26,8 +26,10 @@
 //
 // Algorithmic bytes per launch: nnz*(V+I) + (n+1)*I + n_cols*k*V + n*k*V.
 #include <cstdlib>
+#include <cstdio>
 
 #include "internal.h"
+#include "spmm.cuh"
 #include "tma.cuh"
 
 namespace gkob200 {
@@ -218,75 +220,6 @@ __global__ void __launch_bounds__(kRowsPerCta)
 }
 
 // ---------------------------------------------------------------------------
-// row-block kernel, many right-hand sides (SpMM): one warp per row, lanes over
-// the right-hand-side columns, (col,val) broadcast from shared memory; b and c
-// rows are contiguous (row-major) so every access is a full 128B/256B line.
-// ---------------------------------------------------------------------------
-template <typename V, typename I, bool Advanced>
-__global__ void __launch_bounds__(kRowsPerCta)
-    csr_spmm_rowblock(int64_t n_rows, const I* __restrict__ row_ptrs, const I* __restrict__ col_idxs,
-                      const V* __restrict__ values, const V* __restrict__ b, int64_t b_stride,
-                      int64_t nrhs, const V* __restrict__ alpha_p, const V* __restrict__ beta_p,
-                      V* __restrict__ c, int64_t c_stride, int cap)
-{
-    // 4 warps per CTA; the CTA owns 32 rows (8 per warp) so that its entry stream
-    // is long enough for coalesced staging.
-    constexpr int kRows = 32;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    V* s_val = reinterpret_cast<V*>(smem_raw);
-    I* s_col = reinterpret_cast<I*>(s_val + cap);
-    __shared__ I s_ptr[kRows + 1];
-
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int64_t row0 = static_cast<int64_t>(blockIdx.x) * kRows;
-    const int nrow = static_cast<int>(min(static_cast<int64_t>(kRows), n_rows - row0));
-    if (tid <= nrow) s_ptr[tid] = row_ptrs[row0 + tid];
-    __syncthreads();
-    const I tile_begin = s_ptr[0], tile_end = s_ptr[nrow];
-    V alpha = V(1), beta = V(0);
-    if (Advanced) {
-        alpha = *alpha_p;
-        beta = *beta_p;
-    }
-    for (int64_t j0 = 0; j0 < nrhs; j0 += 32) {
-        const int64_t j = j0 + lane;
-        const bool live = j < nrhs;
-        V acc[kRows / 4];
-#pragma unroll
-        for (int i = 0; i < kRows / 4; ++i) {
-            const int r = wid * (kRows / 4) + i;
-            acc[i] = (Advanced && live && r < nrow) ? mul_rn(c[(row0 + r) * c_stride + j], beta) : V(0);
-        }
-        for (I chunk = tile_begin; chunk < tile_end; chunk += cap) {
-            const int len = static_cast<int>(min(static_cast<I>(cap), tile_end - chunk));
-            __syncthreads();
-            for (int k = tid; k < len; k += kRowsPerCta) {
-                s_col[k] = col_idxs[chunk + k];
-                s_val[k] = values[chunk + k];
-            }
-            __syncthreads();
-#pragma unroll
-            for (int i = 0; i < kRows / 4; ++i) {
-                const int r = wid * (kRows / 4) + i;
-                if (r >= nrow) continue;
-                const int lo = static_cast<int>(max(s_ptr[r], chunk) - chunk);
-                const int hi = static_cast<int>(min(s_ptr[r + 1], chunk + static_cast<I>(len)) - chunk);
-                for (int k = lo; k < hi; ++k) {
-                    const V v = Advanced ? mul_rn(alpha, s_val[k]) : s_val[k];
-                    const V xv = live ? ldg(b + static_cast<int64_t>(s_col[k]) * b_stride + j) : V(0);
-                    acc[i] = add_rn(acc[i], mul_rn(v, xv));
-                }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < kRows / 4; ++i) {
-            const int r = wid * (kRows / 4) + i;
-            if (live && r < nrow) c[(row0 + r) * c_stride + j] = acc[i];
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------
 // merge-path kernel (single right-hand side)
 // ---------------------------------------------------------------------------
 constexpr int kMpThreads = 256;
@@ -318,7 +251,7 @@ __global__ void __launch_bounds__(kMpThreads)
                    const V* __restrict__ values, const V* __restrict__ b, int64_t b_stride,
                    const V* __restrict__ alpha_p, const V* __restrict__ beta_p, V* __restrict__ c,
                    int64_t c_stride, int64_t* __restrict__ carry_row, V* __restrict__ carry_val,
-                   const int64_t* __restrict__ plan)
+                   const int64_t* __restrict__ plan, float keep_frac)
 {
     __shared__ V s_prod[kMpTile + 1];
     __shared__ I s_rowend[kMpTile + 1];
@@ -354,7 +287,7 @@ __global__ void __launch_bounds__(kMpThreads)
     // matrix are random 32-byte sectors — latency, not bandwidth, is what has to be hidden).
     // Streams are marked evict_first, the gathered vector evict_last (see tma.cuh).
     {
-        const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+        const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last(keep_frac);
         V v[kMpItems], xv[kMpItems];
         I col[kMpItems];
 #pragma unroll
@@ -590,18 +523,21 @@ int csr_spmv_launch(cudaStream_t s, int64_t n_rows, int64_t n_cols, int64_t nnz,
     }
     if (nrhs > 1) {
         if (fused) return GKOB200_EUNSUPPORTED;
-        // SpMM: warp-per-row kernel with lanes over right-hand sides
-        const int cap = 1024;
-        const size_t smem = static_cast<size_t>(cap) * (sizeof(V) + sizeof(I));
-        const int64_t grid = ceildiv(n_rows, 32);
-        if (adv)
-            csr_spmm_rowblock<V, I, true><<<static_cast<unsigned>(grid), kRowsPerCta, smem, s>>>(
-                n_rows, row_ptrs, col_idxs, values, b, b_stride, nrhs, alpha, beta, c, c_stride, cap);
-        else
-            csr_spmm_rowblock<V, I, false><<<static_cast<unsigned>(grid), kRowsPerCta, smem, s>>>(
-                n_rows, row_ptrs, col_idxs, values, b, b_stride, nrhs, alpha, beta, c, c_stride, cap);
-        GKOB200_CHECK_LAUNCH();
-        return 0;
+        // SpMM: warp-tile kernel, lanes over right-hand sides (spmm.cuh)
+#define GKOB200_SPMM_CASE(C)                                                                        \
+    {                                                                                               \
+        spmm::CsrStager<V, I, spmm::C> st{row_ptrs, col_idxs, values, n_rows, 0, 0};                 \
+        return spmm::launch_cfg<V, I, decltype(st), spmm::C>(s, n_rows, st, b, b_stride, nrhs, alpha, \
+                                                             beta, c, c_stride);                    \
+    }
+        switch (spmm::pick_cfg()) {
+        case 1: GKOB200_SPMM_CASE(CfgB)
+        case 2: GKOB200_SPMM_CASE(CfgC)
+        case 3: GKOB200_SPMM_CASE(CfgD)
+        case 4: GKOB200_SPMM_CASE(CfgE)
+        default: GKOB200_SPMM_CASE(CfgA)
+        }
+#undef GKOB200_SPMM_CASE
     }
     if (strategy == GKOB200_CSR_CLASSICAL) {
         const int cap = rowblock_cap(max_block_nnz, sizeof(V) + sizeof(I));
@@ -664,14 +600,31 @@ int csr_spmv_launch(cudaStream_t s, int64_t n_rows, int64_t n_cols, int64_t nnz,
     int64_t* carry_row = reinterpret_cast<int64_t*>(workspace);
     const int64_t* plan = strategy == GKOB200_CSR_MERGE_PATH_PLANNED ? carry_row + n_tiles + 1 : nullptr;
     V* carry_val = reinterpret_cast<V*>(carry_row + 2 * (n_tiles + 1) + 1);
+    static const float keep_frac = [] {
+        if (const char* e = getenv("GKOB200_L2_PERSIST_MB")) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceProp prop;
+            cudaGetDeviceProperties(&prop, dev);
+            size_t want = static_cast<size_t>(atol(e)) << 20, got = 0;
+            cudaError_t rc = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+            cudaDeviceGetLimit(&got, cudaLimitPersistingL2CacheSize);
+            fprintf(stderr, "[gkob200] persisting L2: max %zu MB, window max %zu MB, L2 %zu MB, set %zu MB -> %s, now %zu MB\n",
+                    static_cast<size_t>(prop.persistingL2CacheMaxSize) >> 20,
+                    static_cast<size_t>(prop.accessPolicyMaxWindowSize) >> 20,
+                    static_cast<size_t>(prop.l2CacheSize) >> 20, want >> 20, cudaGetErrorName(rc), got >> 20);
+        }
+        const char* f = getenv("GKOB200_MP_KEEP_FRAC");
+        return f ? static_cast<float>(atof(f)) : 1.0f;
+    }();
     if (adv)
         csr_spmv_merge<V, I, true><<<static_cast<unsigned>(n_tiles), kMpThreads, 0, s>>>(
             n_rows, nnz, row_ptrs, col_idxs, values, b, b_stride, alpha, beta, c, c_stride, carry_row,
-            carry_val, plan);
+            carry_val, plan, keep_frac);
     else
         csr_spmv_merge<V, I, false><<<static_cast<unsigned>(n_tiles), kMpThreads, 0, s>>>(
             n_rows, nnz, row_ptrs, col_idxs, values, b, b_stride, alpha, beta, c, c_stride, carry_row,
-            carry_val, plan);
+            carry_val, plan, keep_frac);
     GKOB200_CHECK_LAUNCH();
     csr_spmv_merge_fixup<V><<<static_cast<unsigned>(ceildiv(n_tiles, 256)), 256, 0, s>>>(
         static_cast<int>(n_tiles), carry_row, carry_val, n_rows, c, c_stride);

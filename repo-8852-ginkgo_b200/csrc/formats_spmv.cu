@@ -12,9 +12,7 @@
 // rounded product + rounded sum: bit-identical to the reference executor.  Padding
 // entries (col == -1) are skipped like the reference does.
 //
-// Multi-RHS (SpMM): a warp owns 32 rows x 32 right-hand sides; lane = RHS column, the
-// (col,val) of the 32 rows are loaded coalesced once per stored column and broadcast
-// with shuffles, every b / c access is one full contiguous line.
+// Multi-RHS (SpMM): spmm.cuh (warp tiles walked row by row, lane = RHS column).
 //
 // COO (accumulating spmv2, row-sorted): nnz are split evenly over CTAs and threads;
 // products are staged coalesced into shared memory, each thread reduces its run of
@@ -25,6 +23,7 @@
 // Algorithmic bytes: ELL n*w*(V+I) + (n_cols+n)*k*V;
 // SELL-P S*(V+I) + (ns+1)*8 + (n_cols+n)*k*V; COO nnz*(V+2I) + n_cols*k*V + 2*n*k*V.
 #include "internal.h"
+#include "spmm.cuh"
 
 namespace gkob200 {
 namespace {
@@ -101,54 +100,6 @@ __global__ void __launch_bounds__(256)
     if (Fused && fu.out) store_block_partial(live ? acc * fu.w[r] : V(0), ws_partials<V>(fu.ws));
 }
 
-// SpMM: warp = 32 rows x 32 RHS columns (lane = RHS column)
-template <typename V, typename I, typename Fmt, bool Advanced>
-__global__ void __launch_bounds__(128)
-    strided_spmm(int64_t n_rows, Fmt fmt, const I* __restrict__ cols, const V* __restrict__ vals,
-                 const V* __restrict__ b, int64_t b_stride, int64_t nrhs, const V* __restrict__ alpha_p,
-                 const V* __restrict__ beta_p, V* __restrict__ c, int64_t c_stride)
-{
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
-    const int64_t row0 = warp * 32;
-    if (row0 >= n_rows) return;
-    const int64_t my_row = row0 + lane;  // the row whose (col,val) this lane fetches
-    int64_t first = 0, step = 0, len = 0;
-    if (my_row < n_rows) fmt.row(my_row, first, step, len);
-    int64_t max_len = len;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) max_len = max(max_len, __shfl_xor_sync(0xffffffffu, max_len, o));
-    const int nr = static_cast<int>(min(static_cast<int64_t>(32), n_rows - row0));
-    V alpha = V(1), beta = V(0);
-    if (Advanced) {
-        alpha = *alpha_p;
-        beta = *beta_p;
-    }
-    for (int64_t j0 = 0; j0 < nrhs; j0 += 32) {
-        const int64_t j = j0 + lane;
-        const bool jl = j < nrhs;
-        V acc[32];
-#pragma unroll
-        for (int r = 0; r < 32; ++r)
-            acc[r] = (Advanced && jl && r < nr) ? mul_rn(c[(row0 + r) * c_stride + j], beta) : V(0);
-        for (int64_t i = 0; i < max_len; ++i) {
-            const bool in = i < len;
-            const I mycol = in ? cols[first + i * step] : I(-1);
-            V myval = in ? vals[first + i * step] : V(0);
-            if (Advanced) myval = mul_rn(alpha, myval);
-#pragma unroll
-            for (int r = 0; r < 32; ++r) {
-                const I col = __shfl_sync(0xffffffffu, mycol, r);
-                const V v = __shfl_sync(0xffffffffu, myval, r);
-                if (col != I(-1) && jl) acc[r] = add_rn(acc[r], mul_rn(v, ldg(b + static_cast<int64_t>(col) * b_stride + j)));
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < 32; ++r)
-            if (jl && r < nr) c[(row0 + r) * c_stride + j] = acc[r];
-    }
-}
-
 template <typename V, typename I, typename Fmt>
 int strided_launch(cudaStream_t s, int64_t n_rows, Fmt fmt, const I* cols, const V* vals, const V* b,
                    int64_t b_stride, int64_t nrhs, const V* alpha, const V* beta, V* c, int64_t c_stride,
@@ -157,13 +108,20 @@ int strided_launch(cudaStream_t s, int64_t n_rows, Fmt fmt, const I* cols, const
     const bool adv = alpha != nullptr;
     if (nrhs > 1) {
         if (fusion && fusion->out) return GKOB200_EUNSUPPORTED;
-        const unsigned grid = static_cast<unsigned>(ceildiv(ceildiv(n_rows, 32), 4));
-        if (adv)
-            strided_spmm<V, I, Fmt, true><<<grid, 128, 0, s>>>(n_rows, fmt, cols, vals, b, b_stride, nrhs, alpha, beta, c, c_stride);
-        else
-            strided_spmm<V, I, Fmt, false><<<grid, 128, 0, s>>>(n_rows, fmt, cols, vals, b, b_stride, nrhs, alpha, beta, c, c_stride);
-        GKOB200_CHECK_LAUNCH();
-        return 0;
+#define GKOB200_SPMM_CASE(C)                                                                        \
+    {                                                                                               \
+        spmm::StridedStager<V, I, Fmt, spmm::C> st{fmt, cols, vals, n_rows, 0, 0, 0, 0};            \
+        return spmm::launch_cfg<V, I, decltype(st), spmm::C>(s, n_rows, st, b, b_stride, nrhs, alpha, \
+                                                             beta, c, c_stride);                    \
+    }
+        switch (spmm::pick_cfg()) {
+        case 1: GKOB200_SPMM_CASE(CfgB)
+        case 2: GKOB200_SPMM_CASE(CfgC)
+        case 3: GKOB200_SPMM_CASE(CfgD)
+        case 4: GKOB200_SPMM_CASE(CfgE)
+        default: GKOB200_SPMM_CASE(CfgA)
+        }
+#undef GKOB200_SPMM_CASE
     }
     SpmvFusion<V> fu;
     if (fusion) fu = *fusion;

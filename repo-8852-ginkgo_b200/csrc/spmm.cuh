@@ -1,0 +1,369 @@
+// spmm.cuh — multi-right-hand-side SpMV (SpMM) for CSR, ELL and SELL-P on sm_100a.
+//
+// Replaces the nrhs > 1 branch of gko::kernels::cuda::{csr,ell,sellp}::spmv/advanced_spmv
+// (reference common/cuda_hip/matrix/csr_kernels.hpp.inc abstract_classical_spmv,
+// ell_kernels.hpp.inc:42-190, sellp_kernels.hpp.inc:47-134) and follows the arithmetic of
+// reference/matrix/{csr,ell,sellp}_kernels.cpp: per (row, column) the products are added in
+// storage order with a rounded multiply and a rounded add, so results are bit-identical.
+//
+// Dense operands are row-major, so a row of b with 32 fp32 columns is exactly one 128-byte
+// line and every stored entry needs one full line of b: 58 GB of line requests for the
+// 27-pt 256^3 matrix against 7.9 GB of algorithmic DRAM bytes.  The kernel is bound by the
+// L2 -> SM fabric (about 7 TB/s measured on B200, profiles/), i.e. by the L1 hit rate of
+// those requests, and ncu shows L1 only retains a line over a reuse distance of a few
+// hundred lines per SM.  Hence:
+//   * lane = right-hand-side column; a warp owns a tile of kTileRows consecutive rows and
+//     walks it ENTRY-MAJOR (entry k of all rows, then entry k+1) with one accumulator per
+//     row: for banded matrices entry k+1 of row r is the line entry k of row r+1 just
+//     fetched, so the reuse distance is kTileRows lines per warp;
+//   * the (col,val) pairs of a tile are staged coalesced into shared memory in that
+//     entry-major order and read back as 128-bit broadcasts (4 rows per LDS);
+//   * a tile whose rows all have the same length and no padding runs without predicates;
+//   * address = one IMAD.WIDE (32-bit column x row pitch in bytes + pointer).
+#pragma once
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace gkob200 {
+namespace spmm {
+
+constexpr int kMaxLen = 36;                       // longest staged row; longer rows take the unstaged path
+constexpr int kMaxPasses = 16;                    // consecutive passes (kWarps tiles each) per CTA
+
+// kWarps warps per CTA, kTileRows rows per warp tile, kBatch independent line loads per warp
+// before the first add, kMinCtas resident CTAs per SM (register budget)
+template <int W, int T, int B, int M, bool H = false>
+struct Cfg {
+    static constexpr int kWarps = W, kTileRows = T, kBatch = B, kMinCtas = M;
+    static constexpr bool kHint = H;
+    static constexpr int kTileCap = T * kMaxLen;     // staged entries per warp
+};
+
+// b is the reused operand: ask L1 to keep its lines (evict_last); the (col,val) streams are
+// read once and must not displace them (no_allocate).
+template <bool Hint>
+__device__ __forceinline__ float ld_b(const float* p)
+{
+    if (!Hint) return ldg(p);
+    float v;
+    asm volatile("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+template <bool Hint>
+__device__ __forceinline__ double ld_b(const double* p)
+{
+    if (!Hint) return ldg(p);
+    double v;
+    asm volatile("ld.global.nc.L1::evict_last.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ld_stream(const float* p)
+{
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ld_stream(const double* p)
+{
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int32_t ld_stream(const int32_t* p)
+{
+    int32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int64_t ld_stream(const int64_t* p)
+{
+    int64_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
+// Both stagers produce the same layout: entry k of row r of the tile is s_col / s_val
+// [k * kTileRows + r] for k < max_len; slots past the end of a row hold col = -1, val = 0.
+// stage() returns true when the tile is "clean": no such slot and no padding entry.
+//
+// CSR: lane (r = lane % kTileRows, q = lane / kTileRows) copies entries q, q + 32/kTileRows,
+// ... of row r: 16-byte pieces of kTileRows neighbouring rows per load instruction, the other
+// half of each sector is picked up from L1 by the next one; the stores are conflict-free.
+template <typename V, typename I, typename C>
+struct CsrStager {
+    static constexpr int kTileRows = C::kTileRows;
+    const I* row_ptrs;
+    const I* cols;
+    const V* vals;
+    int64_t n_rows;
+    // per-lane state
+    int64_t ptr;    // row_ptrs[row0 + lane] for lane <= nr
+    int max_len;
+
+    __device__ __forceinline__ void begin_tile(int64_t row0, int nr, int lane)
+    {
+        ptr = row_ptrs[row0 + min(lane, nr)];
+        max_len = static_cast<int>(min(__shfl_down_sync(0xffffffffu, ptr, 1) - ptr, static_cast<int64_t>(1) << 30));
+        if (lane >= nr) max_len = 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) max_len = max(max_len, __shfl_xor_sync(0xffffffffu, max_len, o));
+    }
+    __device__ __forceinline__ bool single_chunk() const { return max_len <= kMaxLen; }
+    __device__ __forceinline__ bool stage(I* s_col, V* s_val, int lane) const
+    {
+        const int r = lane % kTileRows;
+        const int64_t first = __shfl_sync(0xffffffffu, ptr, r);
+        const int len = static_cast<int>(__shfl_sync(0xffffffffu, ptr, r + 1) - first);
+        for (int k = lane / kTileRows; k < max_len; k += 32 / kTileRows) {
+            const bool in = k < len;
+            s_col[k * kTileRows + r] = in ? cols[first + k] : I(-1);
+            s_val[k * kTileRows + r] = in ? vals[first + k] : V(0);
+        }
+        return __all_sync(0xffffffffu, len == max_len);
+    }
+    __device__ __forceinline__ void row_entries(int r, int64_t& first, int64_t& step, int64_t& len) const
+    {
+        first = __shfl_sync(0xffffffffu, ptr, r);
+        step = 1;
+        len = __shfl_sync(0xffffffffu, ptr, r + 1) - first;
+    }
+};
+
+// ELL / SELL-P: a row's entries are `step` apart; lanes (r = lane % kTileRows, kk = lane / kTileRows)
+// load kTileRows consecutive rows x 32/kTileRows stored columns per instruction.
+template <typename V, typename I, typename Fmt, typename C>
+struct StridedStager {
+    static constexpr int kTileRows = C::kTileRows;
+    Fmt fmt;
+    const I* cols;
+    const V* vals;
+    int64_t n_rows;
+    int64_t first, step, len;   // of row (row0 + (lane & 15))
+    int64_t max_len;
+
+    __device__ __forceinline__ void begin_tile(int64_t row0, int nr, int lane)
+    {
+        const int r = lane & (kTileRows - 1);
+        first = step = len = 0;
+        if (r < nr) fmt.row(row0 + r, first, step, len);
+        max_len = len;
+#pragma unroll
+        for (int o = kTileRows / 2; o > 0; o >>= 1) max_len = max(max_len, __shfl_xor_sync(0xffffffffu, max_len, o));
+    }
+    __device__ __forceinline__ bool single_chunk() const { return max_len <= kMaxLen; }
+    __device__ __forceinline__ bool stage(I* s_col, V* s_val, int lane) const
+    {
+        const int r = lane & (kTileRows - 1);
+        const int n = static_cast<int>(max_len);
+        bool pad = false;
+        for (int k = lane / kTileRows; k < n; k += 32 / kTileRows) {
+            const bool in = k < len;
+            const I col = !in ? I(-1) : C::kHint ? ld_stream(cols + first + k * step) : cols[first + k * step];
+            s_col[k * kTileRows + r] = col;
+            s_val[k * kTileRows + r] = !in ? V(0) : C::kHint ? ld_stream(vals + first + k * step) : vals[first + k * step];
+            pad |= col < I(0);
+        }
+        return !__any_sync(0xffffffffu, pad);
+    }
+    __device__ __forceinline__ void row_entries(int r, int64_t& first_r, int64_t& step_r, int64_t& len_r) const
+    {
+        first_r = __shfl_sync(0xffffffffu, first, r);
+        step_r = __shfl_sync(0xffffffffu, step, r);
+        len_r = __shfl_sync(0xffffffffu, len, r);
+    }
+};
+
+// address of b[col, j]: one IMAD.WIDE.U32 (32-bit column x 32-bit row pitch in bytes + pointer)
+template <typename V>
+__device__ __forceinline__ const V* b_row(const V* b_j, int32_t col, uint32_t pitch_bytes)
+{
+    return reinterpret_cast<const V*>(reinterpret_cast<const char*>(b_j) +
+                                      static_cast<uint64_t>(static_cast<uint32_t>(col)) * pitch_bytes);
+}
+template <typename V>
+__device__ __forceinline__ const V* b_row(const V* b_j, int64_t col, uint32_t pitch_bytes)
+{
+    return reinterpret_cast<const V*>(reinterpret_cast<const char*>(b_j) + col * static_cast<int64_t>(pitch_bytes));
+}
+
+// kN consecutive shared-memory elements (16-byte aligned) with 128-bit loads
+template <int kN, typename T>
+__device__ __forceinline__ void lds_vec(const T* p, T (&out)[kN])
+{
+    constexpr int per = 16 / sizeof(T);
+    static_assert(kN % per == 0, "batch must be a whole number of 16-byte vectors");
+#pragma unroll
+    for (int q = 0; q < kN / per; ++q) {
+        union {
+            uint4 raw;
+            T t[per];
+        } u;
+        u.raw = reinterpret_cast<const uint4*>(p)[q];
+#pragma unroll
+        for (int i = 0; i < per; ++i) out[q * per + i] = u.t[i];
+    }
+}
+
+// One staged entry slot of all kTileRows rows: acc[r] += val[r] * b[col[r], j].
+// Checked = false: every slot is a real entry — no predicates.
+template <bool Checked, bool Advanced, bool Hint, int kTileRows, typename V, typename I>
+__device__ __forceinline__ void entry_step(V (&acc)[kTileRows], const I* s_col, const V* s_val, const V* b_j,
+                                           uint32_t b_pitch, V alpha)
+{
+    I col[kTileRows];
+    V v[kTileRows], xv[kTileRows];
+    lds_vec(s_col, col);
+    lds_vec(s_val, v);
+#pragma unroll
+    for (int r = 0; r < kTileRows; ++r)
+        xv[r] = ld_b<Hint>(b_row(b_j, Checked && col[r] < I(0) ? I(0) : col[r], b_pitch));
+#pragma unroll
+    for (int r = 0; r < kTileRows; ++r) {
+        const V p = Advanced ? mul_rn(mul_rn(alpha, v[r]), xv[r]) : mul_rn(v[r], xv[r]);
+        acc[r] = (!Checked || col[r] >= I(0)) ? add_rn(acc[r], p) : acc[r];
+    }
+}
+
+template <typename V, typename I, typename Stager, typename C, bool Advanced>
+__global__ void __launch_bounds__(C::kWarps * 32, C::kMinCtas)
+    spmm_tiles(int64_t n_rows, Stager st, const V* __restrict__ b, uint32_t b_pitch, int64_t nrhs,
+               const V* __restrict__ alpha_p, const V* __restrict__ beta_p, V* __restrict__ c,
+               int64_t c_stride, int passes)
+{
+    constexpr int kWarps = C::kWarps, kTileRows = C::kTileRows, kTileCap = C::kTileCap;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    V* s_val = reinterpret_cast<V*>(smem_raw) + wid * kTileCap;
+    I* s_col = reinterpret_cast<I*>(reinterpret_cast<V*>(smem_raw) + kWarps * kTileCap) + wid * kTileCap;
+    V alpha = V(1), beta = V(0);
+    if (Advanced) {
+        alpha = *alpha_p;
+        beta = *beta_p;
+    }
+    const int64_t n_tiles = (n_rows + kTileRows - 1) / kTileRows;
+    const int64_t cta_tile0 = static_cast<int64_t>(blockIdx.x) * kWarps * passes;
+    for (int pass = 0; pass < passes; ++pass) {
+        const int64_t tile = cta_tile0 + static_cast<int64_t>(pass) * kWarps + wid;
+        if (tile >= n_tiles) break;
+        const int64_t row0 = tile * kTileRows;
+        const int nr = static_cast<int>(min(static_cast<int64_t>(kTileRows), n_rows - row0));
+        st.begin_tile(row0, nr, lane);
+        if (st.single_chunk()) {
+            // the whole tile fits the staging buffer (the usual case)
+            __syncwarp();
+            const bool clean = st.stage(s_col, s_val, lane);
+            __syncwarp();
+            const int n_k = static_cast<int>(st.max_len);
+            for (int64_t j0 = 0; j0 < nrhs; j0 += 32) {
+                const bool jl = j0 + lane < nrhs;
+                const int64_t j = jl ? j0 + lane : 0;
+                const V* b_j = b + j;
+                V acc[kTileRows];
+#pragma unroll
+                for (int r = 0; r < kTileRows; ++r)
+                    acc[r] = (Advanced && r < nr) ? mul_rn(c[(row0 + r) * c_stride + j], beta) : V(0);
+                if (clean) {
+#pragma unroll 2
+                    for (int k = 0; k < n_k; ++k)
+                        entry_step<false, Advanced, C::kHint>(acc, s_col + k * kTileRows, s_val + k * kTileRows, b_j,
+                                                              b_pitch, alpha);
+                } else {
+                    for (int k = 0; k < n_k; ++k)
+                        entry_step<true, Advanced, C::kHint>(acc, s_col + k * kTileRows, s_val + k * kTileRows, b_j,
+                                                             b_pitch, alpha);
+                }
+#pragma unroll
+                for (int r = 0; r < kTileRows; ++r)
+                    if (jl && r < nr) c[(row0 + r) * c_stride + j] = acc[r];
+            }
+            continue;
+        }
+        // long rows: no staging; per row the lanes fetch 32 entries at a time and broadcast them
+        for (int64_t j0 = 0; j0 < nrhs; j0 += 32) {
+            const bool jl = j0 + lane < nrhs;
+            const int64_t j = jl ? j0 + lane : 0;
+            const V* b_j = b + j;
+            for (int r = 0; r < nr; ++r) {
+                int64_t first, step, len;
+                st.row_entries(r, first, step, len);
+                V* c_rj = c + (row0 + r) * c_stride + j;
+                V acc = Advanced ? mul_rn(*c_rj, beta) : V(0);
+                for (int64_t k0 = 0; k0 < len; k0 += 32) {
+                    const bool in = k0 + lane < len;
+                    const I mycol = in ? st.cols[first + (k0 + lane) * step] : I(-1);
+                    const V myval = in ? st.vals[first + (k0 + lane) * step] : V(0);
+                    const int n = static_cast<int>(min(static_cast<int64_t>(32), len - k0));
+                    for (int u = 0; u < n; ++u) {
+                        const I col = __shfl_sync(0xffffffffu, mycol, u);
+                        const V v = __shfl_sync(0xffffffffu, myval, u);
+                        if (col >= I(0)) {
+                            const V xv = ldg(b_row(b_j, col, b_pitch));
+                            acc = add_rn(acc, Advanced ? mul_rn(mul_rn(alpha, v), xv) : mul_rn(v, xv));
+                        }
+                    }
+                }
+                if (jl) *c_rj = acc;
+            }
+        }
+    }
+}
+
+// one-time attributes of one kernel instantiation (keyed by the kernel itself)
+template <auto Kernel>
+cudaError_t prepare(size_t smem, int carveout_pct)
+{
+    static const cudaError_t rc = [&] {
+        cudaError_t e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(Kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_pct);
+        return e;
+    }();
+    return rc;
+}
+
+template <typename V, typename I, typename Stager, typename C>
+int launch_cfg(cudaStream_t s, int64_t n_rows, const Stager& st, const V* b, int64_t b_stride, int64_t nrhs,
+               const V* alpha, const V* beta, V* c, int64_t c_stride)
+{
+    constexpr int kWarps = C::kWarps, kTileRows = C::kTileRows, kTileCap = C::kTileCap;
+    if (b_stride * sizeof(V) > 0xffffffffull) return GKOB200_EUNSUPPORTED;
+    const int64_t n_tiles = ceildiv(n_rows, static_cast<int64_t>(kTileRows));
+    // a CTA sweeps `passes` consecutive groups of kWarps tiles; fewer passes on small matrices
+    // so that every SM still gets a CTA
+    int passes = static_cast<int>(n_tiles / (static_cast<int64_t>(kWarps) * 2 * C::kMinCtas * sm_count()));
+    passes = passes < 1 ? 1 : passes > kMaxPasses ? kMaxPasses : passes;
+    if (const char* e = getenv("GKOB200_SPMM_PASSES")) passes = atoi(e) > 0 ? atoi(e) : passes;
+    const unsigned grid = static_cast<unsigned>(ceildiv(n_tiles, static_cast<int64_t>(kWarps) * passes));
+    const size_t smem = static_cast<size_t>(kWarps) * kTileCap * (sizeof(V) + sizeof(I));
+    const uint32_t pitch = static_cast<uint32_t>(b_stride * sizeof(V));
+    // leave the rest of the 256 KB to L1: the kernel lives on L1 hits for b
+    const int carve = static_cast<int>((smem + 1024) * C::kMinCtas * 100 / (228 * 1024)) + 1;
+    if (alpha) {
+        const cudaError_t attr = prepare<spmm_tiles<V, I, Stager, C, true>>(smem, carve);
+        if (attr != cudaSuccess) return static_cast<int>(attr);
+        spmm_tiles<V, I, Stager, C, true><<<grid, kWarps * 32, smem, s>>>(n_rows, st, b, pitch, nrhs, alpha, beta, c, c_stride, passes);
+    } else {
+        const cudaError_t attr = prepare<spmm_tiles<V, I, Stager, C, false>>(smem, carve);
+        if (attr != cudaSuccess) return static_cast<int>(attr);
+        spmm_tiles<V, I, Stager, C, false><<<grid, kWarps * 32, smem, s>>>(n_rows, st, b, pitch, nrhs, alpha, beta, c, c_stride, passes);
+    }
+    GKOB200_CHECK_LAUNCH();
+    return 0;
+}
+
+using CfgA = Cfg<16, 8, 0, 2>;
+using CfgB = Cfg<16, 4, 0, 2>;
+using CfgC = Cfg<16, 16, 0, 1>;
+using CfgD = Cfg<8, 8, 0, 2>;
+using CfgE = Cfg<16, 8, 0, 1>;
+inline int pick_cfg()
+{
+    static const int c = [] {
+        const char* e = getenv("GKOB200_SPMM_CFG");
+        return e ? e[0] - 'A' : 0;
+    }();
+    return c;
+}
+
+}  // namespace spmm
+}  // namespace gkob200

@@ -63,10 +63,10 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first()
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
-__device__ __forceinline__ uint64_t l2_policy_evict_last()
+__device__ __forceinline__ uint64_t l2_policy_evict_last(float fraction = 1.0f)
 {
     uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, %1;" : "=l"(p) : "f"(fraction));
     return p;
 }
 __device__ __forceinline__ double ld_hint(const double* a, uint64_t pol)
