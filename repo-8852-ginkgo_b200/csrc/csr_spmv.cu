@@ -524,20 +524,9 @@ int csr_spmv_launch(cudaStream_t s, int64_t n_rows, int64_t n_cols, int64_t nnz,
     if (nrhs > 1) {
         if (fused) return GKOB200_EUNSUPPORTED;
         // SpMM: warp-tile kernel, lanes over right-hand sides (spmm.cuh)
-#define GKOB200_SPMM_CASE(C)                                                                        \
-    {                                                                                               \
-        spmm::CsrStager<V, I, spmm::C> st{row_ptrs, col_idxs, values, n_rows, 0, 0};                 \
-        return spmm::launch_cfg<V, I, decltype(st), spmm::C>(s, n_rows, st, b, b_stride, nrhs, alpha, \
-                                                             beta, c, c_stride);                    \
-    }
-        switch (spmm::pick_cfg()) {
-        case 1: GKOB200_SPMM_CASE(CfgB)
-        case 2: GKOB200_SPMM_CASE(CfgC)
-        case 3: GKOB200_SPMM_CASE(CfgD)
-        case 4: GKOB200_SPMM_CASE(CfgE)
-        default: GKOB200_SPMM_CASE(CfgA)
-        }
-#undef GKOB200_SPMM_CASE
+        spmm::CsrStager<V, I, spmm::Default> st{row_ptrs, col_idxs, values, n_rows, 0, 0};
+        return spmm::launch_cfg<V, I, decltype(st), spmm::Default>(s, n_rows, st, b, b_stride, nrhs, alpha, beta, c,
+                                                                   c_stride);
     }
     if (strategy == GKOB200_CSR_CLASSICAL) {
         const int cap = rowblock_cap(max_block_nnz, sizeof(V) + sizeof(I));

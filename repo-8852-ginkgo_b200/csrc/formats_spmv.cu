@@ -108,20 +108,9 @@ int strided_launch(cudaStream_t s, int64_t n_rows, Fmt fmt, const I* cols, const
     const bool adv = alpha != nullptr;
     if (nrhs > 1) {
         if (fusion && fusion->out) return GKOB200_EUNSUPPORTED;
-#define GKOB200_SPMM_CASE(C)                                                                        \
-    {                                                                                               \
-        spmm::StridedStager<V, I, Fmt, spmm::C> st{fmt, cols, vals, n_rows, 0, 0, 0, 0};            \
-        return spmm::launch_cfg<V, I, decltype(st), spmm::C>(s, n_rows, st, b, b_stride, nrhs, alpha, \
-                                                             beta, c, c_stride);                    \
-    }
-        switch (spmm::pick_cfg()) {
-        case 1: GKOB200_SPMM_CASE(CfgB)
-        case 2: GKOB200_SPMM_CASE(CfgC)
-        case 3: GKOB200_SPMM_CASE(CfgD)
-        case 4: GKOB200_SPMM_CASE(CfgE)
-        default: GKOB200_SPMM_CASE(CfgA)
-        }
-#undef GKOB200_SPMM_CASE
+        spmm::StridedStager<V, I, Fmt, spmm::Default> st{fmt, cols, vals, n_rows, 0, 0, 0, 0};
+        return spmm::launch_cfg<V, I, decltype(st), spmm::Default>(s, n_rows, st, b, b_stride, nrhs, alpha, beta, c,
+                                                                   c_stride);
     }
     SpmvFusion<V> fu;
     if (fusion) fu = *fusion;

@@ -31,57 +31,14 @@ namespace spmm {
 constexpr int kMaxLen = 36;                       // longest staged row; longer rows take the unstaged path
 constexpr int kMaxPasses = 16;                    // consecutive passes (kWarps tiles each) per CTA
 
-// kWarps warps per CTA, kTileRows rows per warp tile, kBatch independent line loads per warp
-// before the first add, kMinCtas resident CTAs per SM (register budget)
-template <int W, int T, int B, int M, bool H = false>
+// kWarps warps per CTA, kTileRows rows per warp tile, kMinCtas resident CTAs per SM (register
+// budget).  Measured on B200 (27-pt 256^3, 32 fp32 RHS): 16 x 8 x 2 = 4.95 ms; 4-row tiles
+// 5.8 ms, 16-row tiles 5.8 ms, half the warps 6.8-7.5 ms.
+template <int W, int T, int M>
 struct Cfg {
-    static constexpr int kWarps = W, kTileRows = T, kBatch = B, kMinCtas = M;
-    static constexpr bool kHint = H;
+    static constexpr int kWarps = W, kTileRows = T, kMinCtas = M;
     static constexpr int kTileCap = T * kMaxLen;     // staged entries per warp
 };
-
-// b is the reused operand: ask L1 to keep its lines (evict_last); the (col,val) streams are
-// read once and must not displace them (no_allocate).
-template <bool Hint>
-__device__ __forceinline__ float ld_b(const float* p)
-{
-    if (!Hint) return ldg(p);
-    float v;
-    asm volatile("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
-}
-template <bool Hint>
-__device__ __forceinline__ double ld_b(const double* p)
-{
-    if (!Hint) return ldg(p);
-    double v;
-    asm volatile("ld.global.nc.L1::evict_last.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ float ld_stream(const float* p)
-{
-    float v;
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ double ld_stream(const double* p)
-{
-    double v;
-    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ int32_t ld_stream(const int32_t* p)
-{
-    int32_t v;
-    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ int64_t ld_stream(const int64_t* p)
-{
-    int64_t v;
-    asm volatile("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(v) : "l"(p));
-    return v;
-}
 
 // Both stagers produce the same layout: entry k of row r of the tile is s_col / s_val
 // [k * kTileRows + r] for k < max_len; slots past the end of a row hold col = -1, val = 0.
@@ -159,9 +116,9 @@ struct StridedStager {
         bool pad = false;
         for (int k = lane / kTileRows; k < n; k += 32 / kTileRows) {
             const bool in = k < len;
-            const I col = !in ? I(-1) : C::kHint ? ld_stream(cols + first + k * step) : cols[first + k * step];
+            const I col = in ? cols[first + k * step] : I(-1);
             s_col[k * kTileRows + r] = col;
-            s_val[k * kTileRows + r] = !in ? V(0) : C::kHint ? ld_stream(vals + first + k * step) : vals[first + k * step];
+            s_val[k * kTileRows + r] = in ? vals[first + k * step] : V(0);
             pad |= col < I(0);
         }
         return !__any_sync(0xffffffffu, pad);
@@ -207,7 +164,7 @@ __device__ __forceinline__ void lds_vec(const T* p, T (&out)[kN])
 
 // One staged entry slot of all kTileRows rows: acc[r] += val[r] * b[col[r], j].
 // Checked = false: every slot is a real entry — no predicates.
-template <bool Checked, bool Advanced, bool Hint, int kTileRows, typename V, typename I>
+template <bool Checked, bool Advanced, int kTileRows, typename V, typename I>
 __device__ __forceinline__ void entry_step(V (&acc)[kTileRows], const I* s_col, const V* s_val, const V* b_j,
                                            uint32_t b_pitch, V alpha)
 {
@@ -217,7 +174,7 @@ __device__ __forceinline__ void entry_step(V (&acc)[kTileRows], const I* s_col, 
     lds_vec(s_val, v);
 #pragma unroll
     for (int r = 0; r < kTileRows; ++r)
-        xv[r] = ld_b<Hint>(b_row(b_j, Checked && col[r] < I(0) ? I(0) : col[r], b_pitch));
+        xv[r] = ldg(b_row(b_j, Checked && col[r] < I(0) ? I(0) : col[r], b_pitch));
 #pragma unroll
     for (int r = 0; r < kTileRows; ++r) {
         const V p = Advanced ? mul_rn(mul_rn(alpha, v[r]), xv[r]) : mul_rn(v[r], xv[r]);
@@ -266,11 +223,11 @@ __global__ void __launch_bounds__(C::kWarps * 32, C::kMinCtas)
                 if (clean) {
 #pragma unroll 2
                     for (int k = 0; k < n_k; ++k)
-                        entry_step<false, Advanced, C::kHint>(acc, s_col + k * kTileRows, s_val + k * kTileRows, b_j,
+                        entry_step<false, Advanced>(acc, s_col + k * kTileRows, s_val + k * kTileRows, b_j,
                                                               b_pitch, alpha);
                 } else {
                     for (int k = 0; k < n_k; ++k)
-                        entry_step<true, Advanced, C::kHint>(acc, s_col + k * kTileRows, s_val + k * kTileRows, b_j,
+                        entry_step<true, Advanced>(acc, s_col + k * kTileRows, s_val + k * kTileRows, b_j,
                                                              b_pitch, alpha);
                 }
 #pragma unroll
@@ -351,19 +308,7 @@ int launch_cfg(cudaStream_t s, int64_t n_rows, const Stager& st, const V* b, int
     return 0;
 }
 
-using CfgA = Cfg<16, 8, 0, 2>;
-using CfgB = Cfg<16, 4, 0, 2>;
-using CfgC = Cfg<16, 16, 0, 1>;
-using CfgD = Cfg<8, 8, 0, 2>;
-using CfgE = Cfg<16, 8, 0, 1>;
-inline int pick_cfg()
-{
-    static const int c = [] {
-        const char* e = getenv("GKOB200_SPMM_CFG");
-        return e ? e[0] - 'A' : 0;
-    }();
-    return c;
-}
+using Default = Cfg<16, 8, 2>;
 
 }  // namespace spmm
 }  // namespace gkob200

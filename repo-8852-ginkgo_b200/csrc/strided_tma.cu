@@ -20,10 +20,71 @@ namespace {
 
 constexpr int kRows = 128;
 
+// address of b[col * stride]: one IMAD.WIDE.U32 (32-bit column x 32-bit pitch in bytes + pointer)
+template <typename V>
+__device__ __forceinline__ const V* b_at(const V* b, int32_t col, uint32_t pitch_bytes)
+{
+    return reinterpret_cast<const V*>(reinterpret_cast<const char*>(b) +
+                                      static_cast<uint64_t>(static_cast<uint32_t>(col)) * pitch_bytes);
+}
+template <typename V>
+__device__ __forceinline__ const V* b_at(const V* b, int64_t col, uint32_t pitch_bytes)
+{
+    return reinterpret_cast<const V*>(reinterpret_cast<const char*>(b) + col * static_cast<int64_t>(pitch_bytes));
+}
+
+// One row out of shared memory: entries idx, idx + step, ... (len of them), summed in storage
+// order with a rounded product and a rounded sum; padding entries (col < 0) are skipped.
+// Full batches of kBatch entries run without bounds predicates: all
+// their gathers are issued before the first add.
+template <bool Advanced, int kBatch, typename V, typename I>
+__device__ __forceinline__ V row_walk(V acc, const I* s_col, const V* s_val, int idx, int step, int len,
+                                      const V* b, uint32_t b_pitch, V alpha)
+{
+    int i = 0;
+    for (; i + kBatch <= len; i += kBatch) {
+        I col[kBatch];
+        V v[kBatch], xv[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            col[u] = s_col[idx + u * step];
+            v[u] = s_val[idx + u * step];
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) xv[u] = ldg(b_at(b, col[u] < I(0) ? I(0) : col[u], b_pitch));
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            // a branch, not a select: it keeps ptxas from sinking the gathers between the adds
+            if (col[u] >= I(0))
+                acc = Advanced ? add_rn(acc, mul_rn(mul_rn(alpha, v[u]), xv[u])) : add_rn(acc, mul_rn(v[u], xv[u]));
+        }
+        idx += kBatch * step;
+    }
+    if (i < len) {
+        I col[kBatch];
+        V v[kBatch], xv[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            const bool in = i + u < len;
+            col[u] = in ? s_col[idx + u * step] : I(-1);
+            v[u] = in ? s_val[idx + u * step] : V(0);
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) xv[u] = ldg(b_at(b, col[u] < I(0) ? I(0) : col[u], b_pitch));
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            // a branch, not a select: it keeps ptxas from sinking the gathers between the adds
+            if (col[u] >= I(0))
+                acc = Advanced ? add_rn(acc, mul_rn(mul_rn(alpha, v[u]), xv[u])) : add_rn(acc, mul_rn(v[u], xv[u]));
+        }
+    }
+    return acc;
+}
+
 template <typename V, typename I, bool Advanced, bool Fused, int kBatch>
-__global__ void __launch_bounds__(kRows)
+__global__ void __launch_bounds__(kRows, 4)
     sellp_spmv_tma(int64_t n_rows, int slice_size, const uint64_t* __restrict__ slice_sets,
-                   const I* __restrict__ cols, const V* __restrict__ vals, const V* __restrict__ b, int64_t b_stride,
+                   const I* __restrict__ cols, const V* __restrict__ vals, const V* __restrict__ b, uint32_t b_pitch,
                    const V* __restrict__ alpha_p, const V* __restrict__ beta_p, V* __restrict__ c, int64_t c_stride,
                    int cap, SpmvFusion<V> fu, int prefetch_tiles, int64_t total_elems)
 {
@@ -74,37 +135,18 @@ __global__ void __launch_bounds__(kRows)
     }
     mbar_wait(&bar, 0);
     if (live) {
-        const int64_t base = (s_set[sl] - s_set[0]) * slice_size + local;
+        const int base = static_cast<int>(s_set[sl] - s_set[0]) * slice_size + local;
         const int len = static_cast<int>(s_set[sl + 1] - s_set[sl]);
-        for (int i = 0; i < len; i += kBatch) {
-            V v[kBatch], xv[kBatch];
-            unsigned valid = 0;
-#pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
-                // same shape as the CSR row-block kernel: value, column and gather of one entry
-                // together, all kBatch gathers issued before the first add
-                const bool in = i + u < len;
-                const I col = in ? s_col[base + static_cast<int64_t>(i + u) * slice_size] : I(-1);
-                v[u] = in ? s_val[base + static_cast<int64_t>(i + u) * slice_size] : V(0);
-                const bool ok = col != I(-1);
-                xv[u] = ok ? ldg(b + static_cast<int64_t>(col) * b_stride) : V(0);
-                valid |= static_cast<unsigned>(ok) << u;
-            }
-#pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
-                if ((valid >> u) & 1u)
-                    acc = Advanced ? add_rn(acc, mul_rn(mul_rn(alpha, v[u]), xv[u])) : add_rn(acc, mul_rn(v[u], xv[u]));
-            }
-        }
+        acc = row_walk<Advanced, kBatch>(acc, s_col, s_val, base, slice_size, len, b, b_pitch, alpha);
         c[row * c_stride] = acc;
     }
     if (Fused && fu.out) store_block_partial(live ? acc * w_row : V(0), ws_partials<V>(fu.ws));
 }
 
 template <typename V, typename I, bool Advanced, bool Fused, int kBatch>
-__global__ void __launch_bounds__(kRows)
+__global__ void __launch_bounds__(kRows, 4)
     ell_spmv_tma(int64_t n_rows, int64_t stride, int width, const I* __restrict__ cols, const V* __restrict__ vals,
-                 const V* __restrict__ b, int64_t b_stride, const V* __restrict__ alpha_p, const V* __restrict__ beta_p,
+                 const V* __restrict__ b, uint32_t b_pitch, const V* __restrict__ alpha_p, const V* __restrict__ beta_p,
                  V* __restrict__ c, int64_t c_stride, SpmvFusion<V> fu, int prefetch_tiles)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -152,24 +194,7 @@ __global__ void __launch_bounds__(kRows)
     }
     mbar_wait(&bar, 0);
     if (live) {
-        for (int i = 0; i < width; i += kBatch) {
-            V v[kBatch], xv[kBatch];
-            unsigned valid = 0;
-#pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
-                const bool in = i + u < width;
-                const I col = in ? s_col[(i + u) * kRows + tid] : I(-1);
-                v[u] = in ? s_val[(i + u) * kRows + tid] : V(0);
-                const bool ok = col != I(-1);
-                xv[u] = ok ? ldg(b + static_cast<int64_t>(col) * b_stride) : V(0);
-                valid |= static_cast<unsigned>(ok) << u;
-            }
-#pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
-                if ((valid >> u) & 1u)
-                    acc = Advanced ? add_rn(acc, mul_rn(mul_rn(alpha, v[u]), xv[u])) : add_rn(acc, mul_rn(v[u], xv[u]));
-            }
-        }
+        acc = row_walk<Advanced, kBatch>(acc, s_col, s_val, tid, kRows, width, b, b_pitch, alpha);
         c[row * c_stride] = acc;
     }
     if (Fused && fu.out) store_block_partial(live ? acc * w_row : V(0), ws_partials<V>(fu.ws));
@@ -194,6 +219,8 @@ int sellp_spmv_tma_launch(cudaStream_t s, int64_t n_rows, int64_t slice_size, co
 {
     if (slice_size != 32 && slice_size != 64 && slice_size != 128) return 0;
     if (max_slice_len <= 0 || reinterpret_cast<uintptr_t>(vals) % 16 || reinterpret_cast<uintptr_t>(cols) % 16) return 0;
+    if (b_stride * sizeof(V) > 0xffffffffull) return 0;
+    const uint32_t pitch = static_cast<uint32_t>(b_stride * sizeof(V));
     const int cap = static_cast<int>(max_slice_len * kRows);
     const size_t smem = align16(static_cast<size_t>(cap) * sizeof(V)) + align16(static_cast<size_t>(cap) * sizeof(I));
     if (smem > kMaxTileBytes) return 0;
@@ -210,13 +237,13 @@ int sellp_spmv_tma_launch(cudaStream_t s, int64_t n_rows, int64_t slice_size, co
     {                                                                                                             \
         auto kern = sellp_spmv_tma<V, I, ADV, FUSED, BATCH>;                                                       \
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTileBytes); \
-        kern<<<grid, kRows, smem, s>>>(n_rows, static_cast<int>(slice_size), slice_sets, cols, vals, b, b_stride,  \
+        kern<<<grid, kRows, smem, s>>>(n_rows, static_cast<int>(slice_size), slice_sets, cols, vals, b, pitch,     \
                                        alpha, beta, c, c_stride, cap, fu, pf, total);                              \
     }
-    const bool wide = max_slice_len > 10;
+    const bool wide = max_slice_len > 8;
     if (wide) {
-        if (adv && fused) GKOB200_SP(true, true, 14) else if (adv) GKOB200_SP(true, false, 14)
-        else if (fused) GKOB200_SP(false, true, 14) else GKOB200_SP(false, false, 14)
+        if (adv && fused) GKOB200_SP(true, true, 9) else if (adv) GKOB200_SP(true, false, 9)
+        else if (fused) GKOB200_SP(false, true, 9) else GKOB200_SP(false, false, 9)
     } else {
         if (adv && fused) GKOB200_SP(true, true, 7) else if (adv) GKOB200_SP(true, false, 7)
         else if (fused) GKOB200_SP(false, true, 7) else GKOB200_SP(false, false, 7)
@@ -235,7 +262,8 @@ int ell_spmv_tma_launch(cudaStream_t s, int64_t n_rows, int64_t stride, int64_t 
                         const V* b, int64_t b_stride, const V* alpha, const V* beta, V* c, int64_t c_stride,
                         const SpmvFusion<V>* fusion)
 {
-    if (width <= 0 || width > 64) return 0;
+    if (width <= 0 || width > 64 || b_stride * sizeof(V) > 0xffffffffull) return 0;
+    const uint32_t pitch = static_cast<uint32_t>(b_stride * sizeof(V));
     if ((stride * sizeof(V)) % 16 || (stride * sizeof(I)) % 16 || reinterpret_cast<uintptr_t>(vals) % 16 ||
         reinterpret_cast<uintptr_t>(cols) % 16)
         return 0;
@@ -253,12 +281,12 @@ int ell_spmv_tma_launch(cudaStream_t s, int64_t n_rows, int64_t stride, int64_t 
     {                                                                                                             \
         auto kern = ell_spmv_tma<V, I, ADV, FUSED, BATCH>;                                                         \
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTileBytes); \
-        kern<<<grid, kRows, smem, s>>>(n_rows, stride, static_cast<int>(width), cols, vals, b, b_stride, alpha,    \
+        kern<<<grid, kRows, smem, s>>>(n_rows, stride, static_cast<int>(width), cols, vals, b, pitch, alpha,       \
                                        beta, c, c_stride, fu, pf);                                                 \
     }
-    if (width > 10) {
-        if (adv && fused) GKOB200_EL(true, true, 14) else if (adv) GKOB200_EL(true, false, 14)
-        else if (fused) GKOB200_EL(false, true, 14) else GKOB200_EL(false, false, 14)
+    if (width > 8) {
+        if (adv && fused) GKOB200_EL(true, true, 9) else if (adv) GKOB200_EL(true, false, 9)
+        else if (fused) GKOB200_EL(false, true, 9) else GKOB200_EL(false, false, 9)
     } else {
         if (adv && fused) GKOB200_EL(true, true, 7) else if (adv) GKOB200_EL(true, false, 7)
         else if (fused) GKOB200_EL(false, true, 7) else GKOB200_EL(false, false, 7)
