@@ -205,11 +205,29 @@ __device__ __forceinline__ void store_block_partial(T v, T* partials)
     const T s = block_sum(v, red_p);
     if (threadIdx.x == 0) partials[blockIdx.x] = s;
 }
-
+// two reductions per CTA: the second array follows the first (gridDim.x entries each)
 template <typename T>
-__global__ void __launch_bounds__(1024) finish_partials(int64_t n, const T* __restrict__ partials, T* out, const int* skip)
+__device__ __forceinline__ void store_block_partial2(T v0, T v1, T* partials)
+{
+    __shared__ T red_p2[2][32];
+    const T s0 = block_sum(v0, red_p2[0]);
+    const T s1 = block_sum(v1, red_p2[1]);
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = s0;
+        partials[gridDim.x + blockIdx.x] = s1;
+    }
+}
+
+// grid = 1 (one reduction) or 2 (second array right behind the first, result to out2)
+template <typename T>
+__global__ void __launch_bounds__(1024) finish_partials(int64_t n, const T* __restrict__ partials, T* out, const int* skip,
+                                                        T* out2 = nullptr)
 {
     if (skip && *skip) return;
+    if (blockIdx.x == 1) {
+        partials += n;
+        out = out2;
+    }
     __shared__ T red[32];
     T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
     int64_t i = threadIdx.x;

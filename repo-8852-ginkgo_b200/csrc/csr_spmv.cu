@@ -100,9 +100,13 @@ __global__ void __launch_bounds__(kRowsPerCta)
     }
     if (tid < nrow) c[(row0 + tid) * c_stride] = acc;
     if (Fused && fu.out) {
-        V t[1] = {tid < nrow ? acc * fu.w[row0 + tid] : V(0)};
+        V t[2] = {tid < nrow ? acc * fu.w[row0 + tid] : V(0), tid < nrow ? acc * acc : V(0)};
         V* out = fu.out;
-        grid_reduce<1>(t, ws_partials<V>(fu.ws), ws_ticket(fu.ws), [out](V(&tot)[1]) { out[0] = tot[0]; });
+        V* out_sq = fu.out_sq;
+        grid_reduce<2>(t, ws_partials<V>(fu.ws), ws_ticket(fu.ws), [out, out_sq](V(&tot)[2]) {
+            out[0] = tot[0];
+            if (out_sq) out_sq[0] = tot[1];
+        });
     }
 }
 
@@ -215,7 +219,10 @@ __global__ void __launch_bounds__(kRowsPerCta)
     if (tid < nrow) c[(row0 + tid) * c_stride] = acc;
     if (Fused && fu.out) {
         // one partial per CTA, summed by finish_partials right after this launch
-        store_block_partial(tid < nrow ? acc * w_row : V(0), ws_partials<V>(fu.ws));
+        if (fu.out_sq)
+            store_block_partial2(tid < nrow ? acc * w_row : V(0), tid < nrow ? acc * acc : V(0), ws_partials<V>(fu.ws));
+        else
+            store_block_partial(tid < nrow ? acc * w_row : V(0), ws_partials<V>(fu.ws));
     }
 }
 
@@ -564,12 +571,13 @@ int csr_spmv_launch(cudaStream_t s, int64_t n_rows, int64_t n_cols, int64_t nnz,
 #undef GKOB200_RBT
             GKOB200_CHECK_LAUNCH();
             if (fused && fu.out) {
-                finish_partials<V><<<1, 1024, 0, s>>>(static_cast<int64_t>(grid), ws_partials<V>(fu.ws), fu.out, fu.skip);
+                finish_partials<V><<<fu.out_sq ? 2 : 1, 1024, 0, s>>>(static_cast<int64_t>(grid), ws_partials<V>(fu.ws),
+                                                                      fu.out, fu.skip, fu.out_sq);
                 GKOB200_CHECK_LAUNCH();
             }
             return 0;
         }
-        if (fused && fu.out && static_cast<int64_t>(grid) > fu.ws_blocks) return GKOB200_EWORKSPACE;
+        if (fused && fu.out && static_cast<int64_t>(grid) * (fu.out_sq ? 2 : 1) > fu.ws_blocks) return GKOB200_EWORKSPACE;
 #define GKOB200_RB(ADV, FUSED)                                                                        \
     csr_spmv_rowblock<V, I, ADV, FUSED><<<grid, kRowsPerCta, smem, s>>>(                              \
         n_rows, row_ptrs, col_idxs, values, b, b_stride, alpha, beta, c, c_stride, cap, fu)

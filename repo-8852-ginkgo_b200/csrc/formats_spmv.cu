@@ -97,7 +97,12 @@ __global__ void __launch_bounds__(256)
         }
         c[r * c_stride] = acc;
     }
-    if (Fused && fu.out) store_block_partial(live ? acc * fu.w[r] : V(0), ws_partials<V>(fu.ws));
+    if (Fused && fu.out) {
+        if (fu.out_sq)
+            store_block_partial2(live ? acc * fu.w[r] : V(0), live ? acc * acc : V(0), ws_partials<V>(fu.ws));
+        else
+            store_block_partial(live ? acc * fu.w[r] : V(0), ws_partials<V>(fu.ws));
+    }
 }
 
 template <typename V, typename I, typename Fmt>
@@ -116,7 +121,7 @@ int strided_launch(cudaStream_t s, int64_t n_rows, Fmt fmt, const I* cols, const
     if (fusion) fu = *fusion;
     const bool fused = fusion != nullptr;
     const unsigned grid = static_cast<unsigned>(ceildiv(n_rows, 256));
-    if (fused && fu.out && static_cast<int64_t>(grid) > fu.ws_blocks) return GKOB200_EWORKSPACE;
+    if (fused && fu.out && static_cast<int64_t>(grid) * (fu.out_sq ? 2 : 1) > fu.ws_blocks) return GKOB200_EWORKSPACE;
 #define GKOB200_ST(ADV, FUSED) \
     strided_spmv<V, I, Fmt, ADV, FUSED><<<grid, 256, 0, s>>>(n_rows, fmt, cols, vals, b, b_stride, alpha, beta, c, c_stride, fu)
     if (adv && fused) GKOB200_ST(true, true);
@@ -126,7 +131,8 @@ int strided_launch(cudaStream_t s, int64_t n_rows, Fmt fmt, const I* cols, const
 #undef GKOB200_ST
     GKOB200_CHECK_LAUNCH();
     if (fused && fu.out) {
-        finish_partials<V><<<1, 1024, 0, s>>>(static_cast<int64_t>(grid), ws_partials<V>(fu.ws), fu.out, fu.skip);
+        finish_partials<V><<<fu.out_sq ? 2 : 1, 1024, 0, s>>>(static_cast<int64_t>(grid), ws_partials<V>(fu.ws), fu.out,
+                                                              fu.skip, fu.out_sq);
         GKOB200_CHECK_LAUNCH();
     }
     return 0;

@@ -15,6 +15,7 @@ struct SpmvFusion {
     const int* skip = nullptr;
     const V* w = nullptr;
     V* out = nullptr;
+    V* out_sq = nullptr;    // optional second fused reduction: sum of result^2 (needs `out`)
     void* ws = nullptr;
     int64_t ws_blocks = 0;  // number of per-block partials `ws` has room for
 };

@@ -15,6 +15,8 @@ bool matrix_apply_fuses_dot(const gkob200_matrix& A, int64_t nrhs)
                            : GKOB200_CSR_MERGE_PATH;
         return strategy == GKOB200_CSR_CLASSICAL;
     }
+    // a hybrid matrix whose COO part is empty (strategy automatic on a regular matrix) is its ELL part
+    if (A.format == GKOB200_FMT_HYBRID) return A.coo_nnz == 0;
     return A.format == GKOB200_FMT_ELL || A.format == GKOB200_FMT_SELLP || A.format == GKOB200_FMT_CSR_ROWS;
 }
 
@@ -31,6 +33,7 @@ int matrix_apply(cudaStream_t s, const gkob200_matrix& A, const V* b, int64_t b_
         if (!matrix_apply_fuses_dot(A, nrhs)) {
             fu.w = nullptr;
             fu.out = nullptr;
+            fu.out_sq = nullptr;
         }
         fp = &fu;
     }
@@ -116,8 +119,8 @@ int matrix_apply(cudaStream_t s, const gkob200_matrix& A, const V* b, int64_t b_
             rc = ell_spmv_launch<V, int32_t>(s, A.n_rows, A.ell_stride, A.ell_width,
                                              static_cast<const int32_t*>(A.ell_col_idxs),
                                              static_cast<const V*>(A.ell_values), b, b_stride, nrhs, alpha, beta, c,
-                                             c_stride, nullptr);
-            if (rc) return rc;
+                                             c_stride, nrhs == 1 && A.coo_nnz == 0 ? fp : nullptr);
+            if (rc || A.coo_nnz == 0) return rc;
             return coo_spmv_launch<V, int32_t>(s, A.n_rows, A.coo_nnz, static_cast<const int32_t*>(A.coo_row_idxs),
                                                static_cast<const int32_t*>(A.coo_col_idxs),
                                                static_cast<const V*>(A.coo_values), b, b_stride, nrhs, alpha, nullptr,
@@ -126,8 +129,8 @@ int matrix_apply(cudaStream_t s, const gkob200_matrix& A, const V* b, int64_t b_
         rc = ell_spmv_launch<V, int64_t>(s, A.n_rows, A.ell_stride, A.ell_width,
                                          static_cast<const int64_t*>(A.ell_col_idxs),
                                          static_cast<const V*>(A.ell_values), b, b_stride, nrhs, alpha, beta, c,
-                                         c_stride, nullptr);
-        if (rc) return rc;
+                                         c_stride, nrhs == 1 && A.coo_nnz == 0 ? fp : nullptr);
+        if (rc || A.coo_nnz == 0) return rc;
         return coo_spmv_launch<V, int64_t>(s, A.n_rows, A.coo_nnz, static_cast<const int64_t*>(A.coo_row_idxs),
                                            static_cast<const int64_t*>(A.coo_col_idxs),
                                            static_cast<const V*>(A.coo_values), b, b_stride, nrhs, alpha, nullptr,

@@ -93,6 +93,8 @@ struct DevBuf {
     size_t bytes = 0;
     int alloc(size_t b)
     {
+        if (p) cudaFree(p);
+        p = nullptr;
         bytes = b;
         if (b == 0) return 0;
         cudaError_t e = cudaMalloc(&p, b);

@@ -7,11 +7,146 @@
 // polls the device-side status every `check_every` iterations and — for GMRES — at every
 // restart boundary.  Kernels issued after a column has stopped are no-ops through the
 // reference's own has_stopped() guards, so the reported iteration count is exact.
-// Any number of right-hand sides.
+// Any number of right-hand sides; BiCGSTAB with one right-hand side and an identity / scalar
+// Jacobi preconditioner runs the fused iteration below.
 #include "solver_common.cuh"
 
 namespace gkob200 {
 namespace {
+
+// ------------------------------------------------------------------------------
+// Fused BiCGSTAB iteration for one right-hand side and an identity or scalar-Jacobi
+// preconditioner: 5 kernels and 16 vector passes per iteration instead of 18 and 27.
+//   bi_step1   p = r + (rho/prev_rho * alpha/omega) (p - omega v)          [+ y = D^-1 p]
+//   SpMV       v = A y            with beta = rr.v reduced inside the SpMV kernel
+//   bi_step2   alpha = rho/beta; s = r - alpha v; ||s||; criterion check    [+ z = D^-1 s]
+//   SpMV       t = A z            with gamma = s.t and t.t reduced inside the SpMV kernel
+//   bi_step3   omega = gamma/(t.t); x += alpha y + omega z; r = s - omega t;
+//              next rho = rr.r and ||r||; ++iter; criterion check
+// Same arithmetic per entry as bicgstab_step_1/2/3 (krylov_kernels.cu); with the identity
+// preconditioner y aliases p and z aliases s (the reference copies them).
+enum { BI_RHO = 0, BI_PREV_RHO, BI_ALPHA, BI_BETA, BI_GAMMA, BI_OMEGA, BI_TT, BI_COUNT };
+
+template <typename V>
+struct BiParams {
+    int64_t n;
+    V* x;
+    int64_t xs;
+    V *r, *rr, *p, *v, *s, *t, *y, *z;
+    const V* inv_diag;  // scalar Jacobi or nullptr
+    V* sc;
+    SolverState* st;
+    uint8_t* stop_status;
+    V* hist;
+    V* tau;
+    const V* orig_tau;
+    V factor;
+    int64_t max_iters;
+    void* ws;
+};
+
+// rho = rr.r, tau = ||r||, first criterion check (start of iteration 0)
+template <typename V>
+__global__ void __launch_bounds__(256) bi_top(BiParams<V> P)
+{
+    V acc[2] = {V(0), V(0)};
+    const int64_t step = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < P.n; i += step) {
+        const V ri = P.r[i];
+        acc[0] += P.rr[i] * ri;
+        acc[1] += ri * ri;
+    }
+    BiParams<V> Q = P;
+    grid_reduce<2>(acc, ws_partials<V>(P.ws), ws_ticket(P.ws), [Q](V(&tot)[2]) {
+        Q.sc[BI_RHO] = tot[0];
+        Q.tau[0] = sqrt_rn(tot[1]);
+        criterion_check(Q.st, 1, Q.tau, Q.orig_tau, Q.factor, Q.max_iters, true, Q.stop_status, Q.hist, true);
+    });
+}
+
+template <typename V, bool Jacobi>
+__global__ void __launch_bounds__(256) bi_step1(BiParams<V> P)
+{
+    if (P.st->stopped) return;
+    const V om = P.sc[BI_OMEGA], prev = P.sc[BI_PREV_RHO];
+    const bool upd = mul_rn(prev, om) != V(0);
+    const V tmp = upd ? div_rn(mul_rn(div_rn(P.sc[BI_RHO], prev), P.sc[BI_ALPHA]), om) : V(0);
+    const int64_t step = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < P.n; i += step) {
+        const V ri = P.r[i];
+        const V pi = upd ? add_rn(ri, mul_rn(tmp, sub_rn(P.p[i], mul_rn(om, P.v[i])))) : ri;
+        P.p[i] = pi;
+        if (Jacobi) P.y[i] = mul_rn(pi, P.inv_diag[i]);
+    }
+}
+
+template <typename V, bool Jacobi>
+__global__ void __launch_bounds__(256) bi_step2(BiParams<V> P)
+{
+    if (P.st->stopped) return;
+    const V be = P.sc[BI_BETA];
+    const V a = be != V(0) ? div_rn(P.sc[BI_RHO], be) : V(0);
+    V acc[1] = {V(0)};
+    const int64_t step = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < P.n; i += step) {
+        const V si = be != V(0) ? sub_rn(P.r[i], mul_rn(a, P.v[i])) : P.r[i];
+        P.s[i] = si;
+        if (Jacobi) P.z[i] = mul_rn(si, P.inv_diag[i]);
+        acc[0] += si * si;
+    }
+    BiParams<V> Q = P;
+    grid_reduce<1>(acc, ws_partials<V>(P.ws), ws_ticket(P.ws), [Q, a](V(&tot)[1]) {
+        Q.sc[BI_ALPHA] = a;
+        Q.tau[0] = sqrt_rn(tot[0]);
+        // mid-iteration check: not finalized, x += alpha y follows once the solver has stopped
+        criterion_check(Q.st, 1, Q.tau, Q.orig_tau, Q.factor, Q.max_iters, false, Q.stop_status, Q.hist, false);
+    });
+}
+
+template <typename V>
+__global__ void __launch_bounds__(256) bi_step3(BiParams<V> P)
+{
+    if (P.st->stopped) return;
+    const V tt = P.sc[BI_TT];
+    const V om = tt != V(0) ? div_rn(P.sc[BI_GAMMA], tt) : V(0);
+    const V a = P.sc[BI_ALPHA];
+    V acc[2] = {V(0), V(0)};
+    const int64_t step = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < P.n; i += step) {
+        P.x[i * P.xs] = add_rn(P.x[i * P.xs], add_rn(mul_rn(a, P.y[i]), mul_rn(om, P.z[i])));
+        const V ri = sub_rn(P.s[i], mul_rn(om, P.t[i]));
+        P.r[i] = ri;
+        acc[0] += P.rr[i] * ri;
+        acc[1] += ri * ri;
+    }
+    BiParams<V> Q = P;
+    grid_reduce<2>(acc, ws_partials<V>(P.ws), ws_ticket(P.ws), [Q, om](V(&tot)[2]) {
+        Q.sc[BI_OMEGA] = om;
+        Q.sc[BI_PREV_RHO] = Q.sc[BI_RHO];
+        Q.sc[BI_RHO] = tot[0];
+        Q.tau[0] = sqrt_rn(tot[1]);
+        criterion_check(Q.st, 1, Q.tau, Q.orig_tau, Q.factor, Q.max_iters, true, Q.stop_status, Q.hist, true);
+    });
+}
+
+// formats without an in-kernel reduction: out[0] = a.b, out[1] = b.b (out1 may be null)
+template <typename V>
+__global__ void __launch_bounds__(256) bi_dots(int64_t n, const V* __restrict__ a, const V* __restrict__ b, V* out0,
+                                               V* out1, const int* skip, void* ws)
+{
+    if (*skip) return;
+    V acc[2] = {V(0), V(0)};
+    const int64_t step = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += step) {
+        const V bi = b[i];
+        acc[0] += a[i] * bi;
+        acc[1] += bi * bi;
+    }
+    grid_reduce<2>(acc, ws_partials<V>(ws), ws_ticket(ws), [out0, out1](V(&tot)[2]) {
+        out0[0] = tot[0];
+        if (out1) out1[0] = tot[1];
+    });
+}
 
 // ------------------------------------------------------------------------------
 template <typename V>
@@ -27,7 +162,109 @@ struct BicgstabSolver : SolverBase<V> {
         int rc = this->init_base();
         if (rc) return rc;
         if ((rc = vecs.alloc(static_cast<size_t>(n) * k * 8 * sizeof(V)))) return rc;
-        return scal.alloc(static_cast<size_t>(k) * 6 * sizeof(V));
+        // fused path: the SpMV kernels leave up to two partials per CTA (128 rows each)
+        ws_blocks = 2 * (ceildiv(n, 128) + 1);
+        if (ws_blocks < kReduceMaxBlocks) ws_blocks = kReduceMaxBlocks;
+        if ((rc = ws.alloc(reduce_ws_bytes(ws_blocks)))) return rc;
+        return scal.alloc(static_cast<size_t>(k > BI_COUNT ? k : BI_COUNT) * 6 * sizeof(V));
+    }
+    int64_t ws_blocks = 0;
+
+    bool fusable() const
+    {
+        return k == 1 && (M.kind == GKOB200_PRECOND_NONE || M.kind == GKOB200_PRECOND_JACOBI_SCALAR);
+    }
+
+    // one SpMV of the fused iteration: out = A in, d0 = w.out and (optionally) d1 = out.out
+    int fused_spmv(cudaStream_t s, const V* in, V* out, const V* w, V* d0, V* d1)
+    {
+        SpmvFusion<V> fu;
+        fu.skip = &this->st()->stopped;
+        const bool fuses = matrix_apply_fuses_dot(A, 1) && A.format != GKOB200_FMT_CSR_ROWS;
+        if (fuses) {
+            fu.w = w;
+            fu.out = d0;
+            fu.out_sq = d1;
+            fu.ws = ws.p;
+            fu.ws_blocks = ws_blocks;
+        }
+        int rc = matrix_apply<V>(s, A, in, 1, 1, nullptr, nullptr, out, 1, &fu);
+        if (rc) return rc;
+        launch_count += fuses ? 2 : 1;
+        if (!fuses) {
+            bi_dots<V><<<grid_for(n, 256, 4), 256, 0, s>>>(n, w, out, d0, d1, fu.skip, ws.p);
+            ++launch_count;
+            GKOB200_CHECK_LAUNCH();
+        }
+        return 0;
+    }
+
+    int apply_fused(cudaStream_t s, const V* b, int64_t bs, V* x, int64_t xs)
+    {
+        V* tag = B::tag();
+        const bool jac = M.kind == GKOB200_PRECOND_JACOBI_SCALAR;
+        BiParams<V> P;
+        P.n = n;
+        P.x = x;
+        P.xs = xs;
+        P.r = vec(0);
+        P.z = jac ? vec(1) : vec(4);
+        P.y = jac ? vec(2) : vec(6);
+        P.v = vec(3);
+        P.s = vec(4);
+        P.t = vec(5);
+        P.p = vec(6);
+        P.rr = vec(7);
+        P.inv_diag = jac ? static_cast<const V*>(M.inv_diag) : nullptr;
+        P.sc = scal.as<V>();
+        P.st = this->st();
+        P.stop_status = this->stat();
+        P.hist = this->hist.template as<V>();
+        P.tau = this->tau();
+        P.orig_tau = this->orig_tau();
+        P.factor = static_cast<V>(stop.reduction_factor);
+        P.max_iters = stop.max_iters;
+        P.ws = ws.p;
+        int rc;
+        if ((rc = this->reset_state(s))) return rc;
+        // r = b - A x, rr = r, p = v = 0, scalars: rho = prev_rho = alpha = omega = 1 (bicgstab_initialize)
+        if ((rc = typed::bicgstab_initialize(tag, s, n, k, b, bs, P.r, P.rr, vec(2), P.s, P.t, vec(1), P.v, P.p, k,
+                                             P.sc + BI_PREV_RHO, P.sc + BI_RHO, P.sc + BI_ALPHA, P.sc + BI_BETA,
+                                             P.sc + BI_GAMMA, P.sc + BI_OMEGA, this->stat())))
+            return rc;
+        if ((rc = matrix_apply<V>(s, A, x, xs, k, this->neg_one(), this->one(), P.r, k, nullptr))) return rc;
+        if ((rc = this->baseline_norm(s, b, bs, P.r, k))) return rc;
+        if ((rc = typed::dense_copy(tag, s, n, k, P.r, k, P.rr, k))) return rc;
+        const int grid = grid_for(n, 256, 6);
+        bi_top<V><<<grid, 256, 0, s>>>(P);
+        GKOB200_CHECK_LAUNCH();
+        launch_count += 5;
+        bool stopped = false;
+        for (int64_t it = 0;; ++it) {
+            if (it % this->chunk == 0 || it > stop.max_iters) {
+                if ((rc = this->poll(s, &stopped))) return rc;
+                if (stopped) break;
+            }
+            if (jac)
+                bi_step1<V, true><<<grid, 256, 0, s>>>(P);
+            else
+                bi_step1<V, false><<<grid, 256, 0, s>>>(P);
+            GKOB200_CHECK_LAUNCH();
+            if ((rc = fused_spmv(s, P.y, P.v, P.rr, P.sc + BI_BETA, nullptr))) return rc;
+            if (jac)
+                bi_step2<V, true><<<grid, 256, 0, s>>>(P);
+            else
+                bi_step2<V, false><<<grid, 256, 0, s>>>(P);
+            GKOB200_CHECK_LAUNCH();
+            if ((rc = fused_spmv(s, P.z, P.t, P.s, P.sc + BI_GAMMA, P.sc + BI_TT))) return rc;
+            bi_step3<V><<<grid, 256, 0, s>>>(P);
+            GKOB200_CHECK_LAUNCH();
+            launch_count += 3;
+        }
+        // stopped by the mid-iteration check: x += alpha y, then mark finalized
+        if ((rc = typed::bicgstab_finalize(tag, s, n, k, x, xs, P.y, k, P.sc + BI_ALPHA, this->stat()))) return rc;
+        launch_count += 2;
+        return this->finish(s);
     }
 
     int apply(cudaStream_t s, const void* b_, int64_t bs, void* x_, int64_t xs) override
@@ -39,6 +276,7 @@ struct BicgstabSolver : SolverBase<V> {
         this->num_iterations = 0;
         if (n == 0) return 0;
         if (!b || !x) return GKOB200_EINVAL;
+        if (fusable()) return apply_fused(s, b, bs, x, xs);
         V *r = vec(0), *z = vec(1), *y = vec(2), *v = vec(3), *s_ = vec(4), *t = vec(5), *p = vec(6), *rr = vec(7);
         V *alpha = sc(0), *beta = sc(1), *gamma = sc(2), *prev_rho = sc(3), *rho = sc(4), *omega = sc(5);
         uint8_t* stat = this->stat();

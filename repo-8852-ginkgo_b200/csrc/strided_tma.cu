@@ -140,7 +140,12 @@ __global__ void __launch_bounds__(kRows, 4)
         acc = row_walk<Advanced, kBatch>(acc, s_col, s_val, base, slice_size, len, b, b_pitch, alpha);
         c[row * c_stride] = acc;
     }
-    if (Fused && fu.out) store_block_partial(live ? acc * w_row : V(0), ws_partials<V>(fu.ws));
+    if (Fused && fu.out) {
+        if (fu.out_sq)
+            store_block_partial2(live ? acc * w_row : V(0), live ? acc * acc : V(0), ws_partials<V>(fu.ws));
+        else
+            store_block_partial(live ? acc * w_row : V(0), ws_partials<V>(fu.ws));
+    }
 }
 
 template <typename V, typename I, bool Advanced, bool Fused, int kBatch>
@@ -197,7 +202,12 @@ __global__ void __launch_bounds__(kRows, 4)
         acc = row_walk<Advanced, kBatch>(acc, s_col, s_val, tid, kRows, width, b, b_pitch, alpha);
         c[row * c_stride] = acc;
     }
-    if (Fused && fu.out) store_block_partial(live ? acc * w_row : V(0), ws_partials<V>(fu.ws));
+    if (Fused && fu.out) {
+        if (fu.out_sq)
+            store_block_partial2(live ? acc * w_row : V(0), live ? acc * acc : V(0), ws_partials<V>(fu.ws));
+        else
+            store_block_partial(live ? acc * w_row : V(0), ws_partials<V>(fu.ws));
+    }
 }
 
 inline int resident_ctas(size_t smem)
@@ -230,7 +240,7 @@ int sellp_spmv_tma_launch(cudaStream_t s, int64_t n_rows, int64_t slice_size, co
     SpmvFusion<V> fu;
     if (fusion) fu = *fusion;
     const bool fused = fusion != nullptr, adv = alpha != nullptr;
-    if (fused && fu.out && static_cast<int64_t>(grid) > fu.ws_blocks) return GKOB200_EWORKSPACE;
+    if (fused && fu.out && static_cast<int64_t>(grid) * (fu.out_sq ? 2 : 1) > fu.ws_blocks) return GKOB200_EWORKSPACE;
     const int pf = sm_count() * resident_ctas(smem);
     const int64_t total = total_cols * slice_size;
 #define GKOB200_SP(ADV, FUSED, BATCH)                                                                             \
@@ -251,7 +261,8 @@ int sellp_spmv_tma_launch(cudaStream_t s, int64_t n_rows, int64_t slice_size, co
 #undef GKOB200_SP
     GKOB200_CHECK_LAUNCH();
     if (fused && fu.out) {
-        finish_partials<V><<<1, 1024, 0, s>>>(static_cast<int64_t>(grid), ws_partials<V>(fu.ws), fu.out, fu.skip);
+        finish_partials<V><<<fu.out_sq ? 2 : 1, 1024, 0, s>>>(static_cast<int64_t>(grid), ws_partials<V>(fu.ws), fu.out,
+                                                              fu.skip, fu.out_sq);
         GKOB200_CHECK_LAUNCH();
     }
     return 1;
@@ -275,7 +286,7 @@ int ell_spmv_tma_launch(cudaStream_t s, int64_t n_rows, int64_t stride, int64_t 
     SpmvFusion<V> fu;
     if (fusion) fu = *fusion;
     const bool fused = fusion != nullptr, adv = alpha != nullptr;
-    if (fused && fu.out && static_cast<int64_t>(grid) > fu.ws_blocks) return GKOB200_EWORKSPACE;
+    if (fused && fu.out && static_cast<int64_t>(grid) * (fu.out_sq ? 2 : 1) > fu.ws_blocks) return GKOB200_EWORKSPACE;
     const int pf = sm_count() * resident_ctas(smem);
 #define GKOB200_EL(ADV, FUSED, BATCH)                                                                             \
     {                                                                                                             \
@@ -294,7 +305,8 @@ int ell_spmv_tma_launch(cudaStream_t s, int64_t n_rows, int64_t stride, int64_t 
 #undef GKOB200_EL
     GKOB200_CHECK_LAUNCH();
     if (fused && fu.out) {
-        finish_partials<V><<<1, 1024, 0, s>>>(static_cast<int64_t>(grid), ws_partials<V>(fu.ws), fu.out, fu.skip);
+        finish_partials<V><<<fu.out_sq ? 2 : 1, 1024, 0, s>>>(static_cast<int64_t>(grid), ws_partials<V>(fu.ws), fu.out,
+                                                              fu.skip, fu.out_sq);
         GKOB200_CHECK_LAUNCH();
     }
     return 1;
