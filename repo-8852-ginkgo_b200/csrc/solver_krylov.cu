@@ -326,6 +326,29 @@ struct BicgstabSolver : SolverBase<V> {
 };
 
 // ------------------------------------------------------------------------------
+// Fused modified Gram-Schmidt step of the GMRES Arnoldi process (one right-hand side):
+//   w -= h_i v_i   and, in the same pass,   h_{i+1} = w . v_{i+1}      (Last: ||w|| instead)
+// — 4 vector passes per basis vector instead of the 5 of compute_dot + sub_scaled, with the
+// first dot w . v_0 reduced inside the SpMV kernel that produces w.  Same arithmetic and the
+// same (sequential) dependency chain as the reference loop (core/solver/gmres.cpp:299-316).
+template <typename V, bool Last>
+__global__ void __launch_bounds__(256) gmres_mgs_step(int64_t n, V* __restrict__ w, const V* __restrict__ vi,
+                                                      const V* __restrict__ vnext, const V* h_i, V* out,
+                                                      const int* skip, void* ws)
+{
+    if (*skip) return;
+    const V h = h_i[0];
+    V acc[1] = {V(0)};
+    const int64_t step = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += step) {
+        const V wi = sub_rn(w[i], mul_rn(h, vi[i]));
+        w[i] = wi;
+        acc[0] += Last ? wi * wi : wi * vnext[i];
+    }
+    grid_reduce<1>(acc, ws_partials<V>(ws), ws_ticket(ws), [out](V(&tot)[1]) { out[0] = Last ? sqrt_rn(tot[0]) : tot[0]; });
+}
+
+// ------------------------------------------------------------------------------
 template <typename V>
 struct GmresSolver : SolverBase<V> {
     using B = SolverBase<V>;
@@ -342,7 +365,48 @@ struct GmresSolver : SolverBase<V> {
         // hessenberg (m+1) x m k | givens_sin m x k | givens_cos m x k | rnc (m+1) x k | y m x k | residual_norm k
         const size_t cnt = static_cast<size_t>((m + 1) * m * k + 2 * m * k + (m + 1) * k + m * k + k);
         if ((rc = small.alloc(cnt * sizeof(V)))) return rc;
+        // fused Arnoldi: the SpMV kernel leaves one partial per CTA (128 rows each)
+        ws_blocks = ceildiv(n, 128) + 1;
+        if (ws_blocks < kReduceMaxBlocks) ws_blocks = kReduceMaxBlocks;
+        if ((rc = ws.alloc(reduce_ws_bytes(ws_blocks)))) return rc;
         return fin.alloc(static_cast<size_t>(k) * sizeof(uint64_t));
+    }
+    int64_t ws_blocks = 0;
+
+    // next_k = A precvec; modified Gram-Schmidt against basis 0..j; hnorm = ||next_k||  (k == 1)
+    int arnoldi_fused(cudaStream_t s, const V* precvec, V* kb, int64_t j, V* hess_iter, int64_t hs)
+    {
+        V* next_k = kb + (j + 1) * n;
+        SpmvFusion<V> fu;
+        fu.skip = &this->st()->stopped;
+        const bool fuses = matrix_apply_fuses_dot(A, 1) && A.format != GKOB200_FMT_CSR_ROWS;
+        if (fuses) {
+            fu.w = kb;
+            fu.out = hess_iter;
+            fu.ws = ws.p;
+            fu.ws_blocks = ws_blocks;
+        }
+        int rc = matrix_apply<V>(s, A, precvec, 1, 1, nullptr, nullptr, next_k, 1, &fu);
+        if (rc) return rc;
+        launch_count += fuses ? 2 : 1;
+        if (!fuses) {
+            bi_dots<V><<<grid_for(n, 256, 4), 256, 0, s>>>(n, kb, next_k, hess_iter, static_cast<V*>(nullptr), fu.skip, ws.p);
+            ++launch_count;
+            GKOB200_CHECK_LAUNCH();
+        }
+        const int grid = grid_for(n, 256, 6);
+        for (int64_t i = 0; i <= j; ++i) {
+            const V* h = hess_iter + i * hs;
+            if (i < j)
+                gmres_mgs_step<V, false><<<grid, 256, 0, s>>>(n, next_k, kb + i * n, kb + (i + 1) * n, h,
+                                                              hess_iter + (i + 1) * hs, fu.skip, ws.p);
+            else
+                gmres_mgs_step<V, true><<<grid, 256, 0, s>>>(n, next_k, kb + i * n, static_cast<const V*>(nullptr), h,
+                                                             hess_iter + (j + 1) * hs, fu.skip, ws.p);
+            GKOB200_CHECK_LAUNCH();
+            ++launch_count;
+        }
+        return 0;
     }
 
     int apply(cudaStream_t s, const void* b_, int64_t bs, void* x_, int64_t xs) override
@@ -410,23 +474,28 @@ struct GmresSolver : SolverBase<V> {
             V* next_k = kb + (restart_iter + 1) * n * k;
             V* hess_iter = hess + restart_iter * k;
             if ((rc = this->precond_apply(s, this_k, k, precvec, k))) return rc;
-            if ((rc = matrix_apply<V>(s, A, precvec, k, k, nullptr, nullptr, next_k, k, nullptr))) return rc;
-            ++launch_count;
-            // modified Gram-Schmidt against all previous basis vectors
-            for (int64_t i = 0; i <= restart_iter; ++i) {
-                V* h = hess_iter + i * hs;
-                V* basis = kb + i * n * k;
-                if ((rc = typed::dense_compute_dot(tag, s, n, k, next_k, k, basis, k, h, ws.p))) return rc;
-                if ((rc = typed::dense_sub_scaled(tag, s, n, k, h, k, basis, k, next_k, k))) return rc;
-                launch_count += 2;
-            }
             V* hnorm = hess_iter + (restart_iter + 1) * hs;
-            if ((rc = typed::dense_compute_norm2(tag, s, n, k, next_k, k, hnorm, ws.p))) return rc;
+            if (k == 1) {
+                if ((rc = arnoldi_fused(s, precvec, kb, restart_iter, hess_iter, hs))) return rc;
+            } else {
+                if ((rc = matrix_apply<V>(s, A, precvec, k, k, nullptr, nullptr, next_k, k, nullptr))) return rc;
+                ++launch_count;
+                // modified Gram-Schmidt against all previous basis vectors
+                for (int64_t i = 0; i <= restart_iter; ++i) {
+                    V* h = hess_iter + i * hs;
+                    V* basis = kb + i * n * k;
+                    if ((rc = typed::dense_compute_dot(tag, s, n, k, next_k, k, basis, k, h, ws.p))) return rc;
+                    if ((rc = typed::dense_sub_scaled(tag, s, n, k, h, k, basis, k, next_k, k))) return rc;
+                    launch_count += 2;
+                }
+                if ((rc = typed::dense_compute_norm2(tag, s, n, k, next_k, k, hnorm, ws.p))) return rc;
+                ++launch_count;
+            }
             if ((rc = typed::dense_inv_scale(tag, s, n, k, hnorm, k, next_k, k))) return rc;
             if ((rc = typed::gmres_hessenberg_qr(tag, s, k, gsin, gcos, rnorm, rnc, hess_iter, hs, restart_iter, fin_it,
                                                  stat)))
                 return rc;
-            launch_count += 3;
+            launch_count += 2;
             ++restart_iter;
         }
         if ((rc = update_x())) return rc;
