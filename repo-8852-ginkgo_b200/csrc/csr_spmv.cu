@@ -330,21 +330,23 @@ __global__ void __launch_bounds__(kMpThreads)
         ri = lo;
         ki = d - lo;
     }
+    // Walk the thread's merge items.  Row results are kept in registers (at most one per
+    // item) until every thread is done with s_prod, then collected in shared memory — the
+    // products' space is reused — stitched across threads there, and written to c as one
+    // coalesced stream: no scattered stores and no read-modify-write of c in this kernel.
     V acc = V(0);
+    V out_val[kMpItems];
+    int out_row[kMpItems];
 #pragma unroll
     for (int it = 0; it < kMpItems; ++it) {
-        if (ri + ki >= tile_items || d + it >= tile_items) break;
+        out_row[it] = -1;
+        out_val[it] = V(0);
+        if (ri + ki >= tile_items || d + it >= tile_items) continue;
         if (ri < n_tile_rows && static_cast<int>(s_rowend[ri]) <= ki) {
-            // row r_begin+ri is complete with what this thread accumulated (plus
-            // carries from earlier threads, applied below through the scan)
-            const int64_t row = r_begin + ri;
-            // mark: write partial into c now; carry-in fix-up follows
-            if (Advanced) {
-                // beta*c must be applied exactly once, by the thread that ends the row
-                c[row * c_stride] = add_rn(mul_rn(c[row * c_stride], *beta_p), acc);
-            } else {
-                c[row * c_stride] = acc;
-            }
+            // row r_begin+ri is complete with what this thread accumulated (plus carries
+            // from earlier threads, added below)
+            out_row[it] = ri;
+            out_val[it] = acc;
             acc = V(0);
             ++ri;
         } else {
@@ -355,11 +357,16 @@ __global__ void __launch_bounds__(kMpThreads)
     // carry-out of this thread: (row it was accumulating into, partial)
     s_scan_row[tid] = ri;
     s_scan_val[tid] = acc;
+    __syncthreads();   // all reads of s_prod done
+    V* s_out = s_prod;
+#pragma unroll
+    for (int it = 0; it < kMpItems; ++it)
+        if (out_row[it] >= 0) s_out[out_row[it]] = out_val[it];
     __syncthreads();
-    // Stitch rows that span threads: the thread that ENDS a row wrote only its own
-    // share; thread t's carry belongs to tile row s_scan_row[t].  A single pass by
-    // the threads, in order, keeps the left-to-right association: the first thread
-    // of each run of equal carry rows adds the run up and applies it.
+    // Stitch rows that span threads: the thread that ENDS a row stored only its own share;
+    // thread t's carry belongs to tile row s_scan_row[t].  The first thread of each run of
+    // equal carry rows adds the run up in thread order (left-to-right association) and
+    // applies it.
     {
         const int my_row = s_scan_row[tid];
         const bool first = (tid == 0) || (s_scan_row[tid - 1] != my_row);
@@ -371,19 +378,21 @@ __global__ void __launch_bounds__(kMpThreads)
                 ++t;
             }
             if (my_row < n_tile_rows) {
-                // the row ends inside this tile (ended by thread t-1 .. or later):
-                // the ending thread stored its own share before; add the carries of
-                // the earlier threads of the run.  Only partial sums of threads
-                // strictly before the ending thread are in `run`, because the ending
-                // thread reset acc to 0 and moved on to the next row.
-                const int64_t row = r_begin + my_row;
-                c[row * c_stride] = add_rn(run, c[row * c_stride]);
+                // the row ends inside this tile: only partial sums of threads strictly before
+                // the ending thread are in `run` (the ending thread reset acc and moved on)
+                s_out[my_row] = add_rn(run, s_out[my_row]);
             } else {
                 // row continues into the next tile: per-CTA carry
                 carry_row[blockIdx.x] = r_begin + my_row;
                 carry_val[blockIdx.x] = run;
             }
         }
+    }
+    __syncthreads();
+    for (int r = tid; r < n_tile_rows; r += kMpThreads) {
+        const int64_t row = r_begin + r;
+        // beta*c is applied exactly once, by the tile in which the row ends
+        c[row * c_stride] = Advanced ? add_rn(mul_rn(c[row * c_stride], *beta_p), s_out[r]) : s_out[r];
     }
     // (the last thread always ends with open row == n_tile_rows, so the leader of
     // that run has written this tile's carry)
