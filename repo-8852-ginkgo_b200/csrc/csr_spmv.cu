@@ -260,11 +260,19 @@ __global__ void __launch_bounds__(kMpThreads)
                    int64_t c_stride, int64_t* __restrict__ carry_row, V* __restrict__ carry_val,
                    const int64_t* __restrict__ plan, float keep_frac)
 {
-    __shared__ V s_prod[kMpTile + 1];
-    __shared__ I s_rowend[kMpTile + 1];
+    // The merge path only cuts the matrix into tiles of equal rows + entries; inside a tile
+    // the row sums are a segmented reduction over the tile's products:
+    //   s_prod[k]  product of entry k (coalesced loads, gathers batched per thread)
+    //   s_head[k]  tile row that STARTS at entry k, or -1
+    // thread t owns the kMpItems consecutive entries [t*kMpItems, ...): it loads them and their
+    // heads with independent shared-memory reads and reduces them in registers (no search, no
+    // dependent shared-memory chain); rows that span threads are stitched in thread order.
+    __shared__ V s_prod[kMpTile];
+    __shared__ int s_head[kMpTile];
     __shared__ int64_t s_range[4];
-    __shared__ V s_scan_val[kMpThreads];
-    __shared__ int s_scan_row[kMpThreads];
+    __shared__ V s_lead[kMpThreads];      // sum of a thread's entries before its first head
+    __shared__ V s_trail[kMpThreads];     // sum of its entries from its last head on
+    __shared__ int s_last[kMpThreads];    // tile row of its last head, -1: no head in the window
 
     const int tid = threadIdx.x;
     const int64_t total = n_rows + nnz;
@@ -275,24 +283,26 @@ __global__ void __launch_bounds__(kMpThreads)
         const int64_t d = tid == 0 ? diag0 : diag1;
         // planned: the tile's split point was computed once per matrix (gkob200_csr_merge_plan_*),
         // otherwise two binary searches over row_ptrs per CTA and per call (24 dependent loads
-        // at 10^7 rows — most of the kernel's time on skewed matrices)
+        // at 10^7 rows)
         const int64_t r = plan ? plan[blockIdx.x + tid] : merge_path_search<I>(d, row_end, n_rows, nnz);
         s_range[tid * 2] = r;
         s_range[tid * 2 + 1] = d - r;
     }
+#pragma unroll
+    for (int u = 0; u < kMpItems; ++u) s_head[tid + u * kMpThreads] = -1;
     __syncthreads();
     const int64_t r_begin = s_range[0], k_begin = s_range[1];
     const int64_t r_end = s_range[2], k_end = s_range[3];
-    const int n_tile_rows = static_cast<int>(r_end - r_begin);
+    const int n_tile_rows = static_cast<int>(r_end - r_begin);   // rows that END in this tile
     const int n_tile_nnz = static_cast<int>(k_end - k_begin);
     V alpha = V(1);
     if (Advanced) alpha = *alpha_p;
 
-    // coalesced staging: products and row-end offsets (relative to k_begin).  Every thread
-    // first issues all its (col, val) loads, then all its gathers, then forms the products:
-    // up to kMpItems independent requests in flight per thread (the gathers of a skewed
-    // matrix are random 32-byte sectors — latency, not bandwidth, is what has to be hidden).
-    // Streams are marked evict_first, the gathered vector evict_last (see tma.cuh).
+    // coalesced staging of the products.  Every thread first issues all its (col, val) loads,
+    // then all its gathers, then forms the products: up to kMpItems independent requests in
+    // flight per thread (the gathers of a skewed matrix are random 32-byte sectors — latency,
+    // not bandwidth, is what has to be hidden).  Streams are marked evict_first, the gathered
+    // vector evict_last (see tma.cuh).
     {
         const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last(keep_frac);
         V v[kMpItems], xv[kMpItems];
@@ -306,87 +316,91 @@ __global__ void __launch_bounds__(kMpThreads)
         }
 #pragma unroll
         for (int u = 0; u < kMpItems; ++u) xv[u] = ld_hint(b + static_cast<int64_t>(col[u]) * b_stride, pol_keep);
+        // heads: tile row r (1 <= r <= n_tile_rows; r == n_tile_rows is the row left open at the
+        // end of the tile) starts where row r-1 ends, if it has an entry in this tile.  Tile
+        // row 0 is open when the tile starts (its head, if any, lies in an earlier tile).
+        for (int r = tid + 1; r <= n_tile_rows; r += kMpThreads) {
+            const int start = static_cast<int>(static_cast<int64_t>(row_end[r_begin + r - 1]) - k_begin);
+            const int end = r < n_tile_rows ? static_cast<int>(static_cast<int64_t>(row_end[r_begin + r]) - k_begin)
+                                            : n_tile_nnz;
+            if (start < end) s_head[start] = r;
+        }
 #pragma unroll
         for (int u = 0; u < kMpItems; ++u) {
             const int k = tid + u * kMpThreads;
-            if (k < n_tile_nnz) s_prod[k] = Advanced ? mul_rn(mul_rn(alpha, v[u]), xv[u]) : mul_rn(v[u], xv[u]);
+            // entries past the end of the tile count as zeros of the open row
+            s_prod[k] = k < n_tile_nnz ? (Advanced ? mul_rn(mul_rn(alpha, v[u]), xv[u]) : mul_rn(v[u], xv[u])) : V(0);
         }
-    }
-    for (int r = tid; r < n_tile_rows; r += kMpThreads) {
-        s_rowend[r] = static_cast<I>(static_cast<int64_t>(row_end[r_begin + r]) - k_begin);
     }
     __syncthreads();
 
-    // second-level split: thread t owns merge items [t*kMpItems, (t+1)*kMpItems) of the tile
-    const int tile_items = n_tile_rows + n_tile_nnz;
-    const int d = min(tid * kMpItems, tile_items);
-    int ri, ki;
-    {
-        int lo = max(d - n_tile_nnz, 0), hi = min(d, n_tile_rows);
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (static_cast<int>(s_rowend[mid]) <= d - mid - 1) lo = mid + 1; else hi = mid;
-        }
-        ri = lo;
-        ki = d - lo;
-    }
-    // Walk the thread's merge items.  Row results are kept in registers (at most one per
-    // item) until every thread is done with s_prod, then collected in shared memory — the
-    // products' space is reused — stitched across threads there, and written to c as one
-    // coalesced stream: no scattered stores and no read-modify-write of c in this kernel.
-    V acc = V(0);
-    V out_val[kMpItems];
-    int out_row[kMpItems];
+    // per-thread segmented reduction in registers
+    V p[kMpItems];
+    int h[kMpItems];
 #pragma unroll
-    for (int it = 0; it < kMpItems; ++it) {
-        out_row[it] = -1;
-        out_val[it] = V(0);
-        if (ri + ki >= tile_items || d + it >= tile_items) continue;
-        if (ri < n_tile_rows && static_cast<int>(s_rowend[ri]) <= ki) {
-            // row r_begin+ri is complete with what this thread accumulated (plus carries
-            // from earlier threads, added below)
-            out_row[it] = ri;
-            out_val[it] = acc;
-            acc = V(0);
-            ++ri;
-        } else {
-            acc = add_rn(acc, s_prod[ki]);
-            ++ki;
-        }
+    for (int u = 0; u < kMpItems; ++u) {
+        p[u] = s_prod[tid * kMpItems + u];
+        h[u] = s_head[tid * kMpItems + u];
     }
-    // carry-out of this thread: (row it was accumulating into, partial)
-    s_scan_row[tid] = ri;
-    s_scan_val[tid] = acc;
-    __syncthreads();   // all reads of s_prod done
+    __syncthreads();   // s_prod is reused for the row results from here on
     V* s_out = s_prod;
-#pragma unroll
-    for (int it = 0; it < kMpItems; ++it)
-        if (out_row[it] >= 0) s_out[out_row[it]] = out_val[it];
+    for (int r = tid; r < n_tile_rows; r += kMpThreads) s_out[r] = V(0);   // empty rows, and rows stitched below
     __syncthreads();
-    // Stitch rows that span threads: the thread that ENDS a row stored only its own share;
-    // thread t's carry belongs to tile row s_scan_row[t].  The first thread of each run of
-    // equal carry rows adds the run up in thread order (left-to-right association) and
-    // applies it.
+    V lead = V(0), acc = V(0);
+    int cur = -1;   // tile row being accumulated; -1: the row open at the start of the window
+#pragma unroll
+    for (int u = 0; u < kMpItems; ++u) {
+        if (h[u] >= 0) {
+            // a row starts here: what was accumulated so far is complete for `cur` unless cur
+            // is the window's leading segment (that one is stitched with earlier threads)
+            if (cur < 0)
+                lead = acc;
+            else
+                s_out[cur] = acc;   // sole contributor: head and next head both in this window
+            cur = h[u];
+            acc = p[u];
+        } else {
+            acc = add_rn(acc, p[u]);
+        }
+    }
+    if (cur < 0) {
+        lead = acc;
+        acc = V(0);
+    }
+    s_lead[tid] = lead;
+    s_trail[tid] = acc;
+    s_last[tid] = cur;
+    if (tid == 0) {
+        // default: no carry (the open row has no entry in this tile yet); overwritten below
+        carry_row[blockIdx.x] = -1;
+        carry_val[blockIdx.x] = V(0);
+    }
+    __syncthreads();
+    // Stitch in thread order (left-to-right association).  The thread holding the last head of
+    // a row adds its trailing sum and the leading sums of the following threads up to and
+    // including the next thread that has a head; thread 0 does the same for the row that was
+    // open when the tile started.
     {
-        const int my_row = s_scan_row[tid];
-        const bool first = (tid == 0) || (s_scan_row[tid - 1] != my_row);
-        if (first) {
-            V run = s_scan_val[tid];
-            int t = tid + 1;
-            while (t < kMpThreads && s_scan_row[t] == my_row) {
-                run = add_rn(run, s_scan_val[t]);
+        auto run_from = [&](V run, int t) {
+            // add lead[t], lead[t+1], ... until (and including) the first thread with a head
+            while (t < kMpThreads) {
+                run = add_rn(run, s_lead[t]);
+                if (s_last[t] >= 0) break;
                 ++t;
             }
-            if (my_row < n_tile_rows) {
-                // the row ends inside this tile: only partial sums of threads strictly before
-                // the ending thread are in `run` (the ending thread reset acc and moved on)
-                s_out[my_row] = add_rn(run, s_out[my_row]);
+            return run;
+        };
+        auto deliver = [&](int row, V run) {
+            if (row < n_tile_rows) {
+                s_out[row] = run;
             } else {
-                // row continues into the next tile: per-CTA carry
-                carry_row[blockIdx.x] = r_begin + my_row;
+                // the row continues into the next tile: per-CTA carry
+                carry_row[blockIdx.x] = r_begin + row;
                 carry_val[blockIdx.x] = run;
             }
-        }
+        };
+        if (tid == 0) deliver(0, run_from(V(0), 0));
+        if (cur >= 0) deliver(cur, run_from(acc, tid + 1));
     }
     __syncthreads();
     for (int r = tid; r < n_tile_rows; r += kMpThreads) {
@@ -394,8 +408,6 @@ __global__ void __launch_bounds__(kMpThreads)
         // beta*c is applied exactly once, by the tile in which the row ends
         c[row * c_stride] = Advanced ? add_rn(mul_rn(c[row * c_stride], *beta_p), s_out[r]) : s_out[r];
     }
-    // (the last thread always ends with open row == n_tile_rows, so the leader of
-    // that run has written this tile's carry)
 }
 
 // split row of every tile diagonal, computed once per matrix
