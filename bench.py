@@ -168,6 +168,16 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def ncu_traffic(fmt, grid):
+    """DRAM read + write bytes per launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/r01_traffic.json; written by tools/ncu_summary.py)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            return json.load(f).get(f"{fmt}_27pt_{grid}")
+    except (OSError, ValueError):
+        return None
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -274,7 +284,8 @@ def main():
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": f"{args.format}_spmv", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src, "frac_of_nominal_8000": achieved / 8000.0,
-                     "bytes_per_launch": spmv_bytes, "us_per_launch": spmv_s * 1e6, "traffic": None},
+                     "bytes_per_launch": spmv_bytes, "us_per_launch": spmv_s * 1e6,
+                     "traffic": ncu_traffic(args.format, g)},
         "cg_iteration": {"us": 1e6 * secs / (args.steps * iters), "model_bytes": it_bytes,
                          "model_gbs": it_bytes * args.steps * iters / secs / 1e9,
                          "frac_of_peak": it_bytes * args.steps * iters / secs / 1e9 / peak},
