@@ -52,7 +52,7 @@ class Communicator:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and lib is not None:  # lib is None while the interpreter shuts down
             lib.gkob200_dist_comm_destroy(h)
 
     def all_reduce_sum(self, t):
@@ -253,7 +253,7 @@ class Matrix(_SparseBase):
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and lib is not None:  # lib is None while the interpreter shuts down
             lib.gkob200_dist_matrix_destroy(h)
 
     def apply(self, *args):

@@ -72,7 +72,7 @@ class _Solver:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and lib is not None:  # lib is None while the interpreter shuts down
             lib.gkob200_solver_destroy(h)
 
     def get_system_matrix(self):

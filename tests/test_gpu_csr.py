@@ -170,3 +170,28 @@ def test_stencils_bit_identical_and_linear(gko, exec_, ora, kind, dims):
     # A * 1 vanishes in the interior of a Laplacian-like stencil
     one, _ = gpu_apply(gko, exec_, rp, ci, va, (n, n), np.ones((n, 1)), "classical")
     assert np.count_nonzero(one) < n
+
+
+@pytest.mark.parametrize("n,row_len", [(40, 30000), (3, 2304), (5000, 1), (2305, 0)])
+def test_merge_path_rows_spanning_many_tiles(gko, exec_, ora, n, row_len):
+    """Tiles of the merge-path kernel hold 2304 merge items: rows far longer than a tile (tiles
+    without any row end, carries through several tiles), rows of exactly one tile, a tile of
+    single-entry rows, and an all-empty matrix; every third row empty in between."""
+    rng = np.random.default_rng(n)
+    m = max(row_len, 7)
+    lens = np.where(np.arange(n) % 3 == 1, 0, row_len).astype(np.int64)
+    rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    ci = np.concatenate([np.sort(rng.choice(m, size=l, replace=False)) for l in lens] + [np.zeros(0, np.int64)]).astype(np.int32)
+    va = rng.uniform(-1, 1, len(ci))
+    b = rng.uniform(-1, 1, (m, 1))
+    want = ora.csr_spmv(rp, ci, va, b)
+    got, A = gpu_apply(gko, exec_, rp, ci, va, (n, m), b, "merge_path")
+    assert A.kernel() == "merge_path"
+    assert (np.abs(got - want) / entry_bound(rp, ci, va, b)).max() <= 1e-12
+    c0 = rng.uniform(-1, 1, (n, 1))
+    want = ora.csr_spmv(rp, ci, va, b, -0.5, 3.0, c0)
+    got, _ = gpu_apply(gko, exec_, rp, ci, va, (n, m), b, "merge_path", -0.5, 3.0, c0)
+    assert (np.abs(got - want) / entry_bound(rp, ci, va, b, -0.5, 3.0, c0)).max() <= 1e-12
+    # twice through the same (planned) descriptor: carries of the first launch must not leak
+    got2, _ = gpu_apply(gko, exec_, rp, ci, va, (n, m), b, "merge_path", -0.5, 3.0, c0)
+    assert np.array_equal(got, got2)

@@ -204,3 +204,46 @@ def test_stencil_formats_agree_and_cg_on_sellp(gko, exec_, ora):
     solver.apply(gko.matrix.Dense.from_numpy(exec_, b), dxs)
     assert abs(solver.num_iterations - it_ref) <= 2
     assert np.abs(dxs.to_numpy()[:, 0] - x_ref).max() <= 1e-9 * np.abs(x_ref).max()
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("nrhs", [2, 32, 37, 64])
+def test_spmm_stencil_all_formats_bit_identical(gko, exec_, ora, dtype, nrhs):
+    """SpMM tile kernel (spmm.cuh): clean tiles (all rows of a warp tile equally long — the
+    predicate-free path), ragged boundary tiles, a partial last tile, several column blocks."""
+    rp, ci, va, n = gko.gen.stencil_csr("27pt", 13, 11, 9, value_dtype=dtype)
+    A = gko.matrix.Csr.from_arrays(exec_, (n, n), rp, ci, va)
+    rng = np.random.default_rng(12)
+    b = rng.uniform(-1, 1, (n, nrhs)).astype(dtype)
+    c0 = rng.uniform(-1, 1, (n, nrhs)).astype(dtype)
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    db = gko.matrix.Dense.from_numpy(exec_, b)
+    for alpha, beta in ((None, None), (-0.75, 2.0)):
+        want = ora.csr_spmv(rp, ci, va, b, alpha, beta, c0 if alpha else None)
+        for fmt in ("csr", "ell", "sellp", "hybrid"):
+            M = A if fmt == "csr" else A.convert_to(fmt, strategy=gko.matrix.HybridStrategy.column_limit(27)) \
+                if fmt == "hybrid" else A.convert_to(fmt)
+            dc = gko.matrix.Dense.from_numpy(exec_, c0)
+            if alpha is None:
+                M.apply(db, dc)
+            else:
+                M.apply(gko.matrix.Dense.scalar(exec_, alpha, tdt), db, gko.matrix.Dense.scalar(exec_, beta, tdt), dc)
+            assert np.array_equal(dc.to_numpy(), want), (fmt, alpha)
+
+
+@pytest.mark.parametrize("fmt", ["csr", "ell", "sellp"])
+def test_spmm_rows_longer_than_the_staging_tile(gko, exec_, ora, fmt):
+    """Rows above 36 entries take the unstaged path of the SpMM kernel; mixed with short and
+    empty rows in the same matrix."""
+    rp, ci, va, A = make(gko, exec_, (700, 650), 0.02, 21, skew=True)
+    M = A if fmt == "csr" else A.convert_to(fmt)
+    rng = np.random.default_rng(5)
+    b = rng.uniform(-1, 1, (650, 33))
+    c0 = rng.uniform(-1, 1, (700, 33))
+    db = gko.matrix.Dense.from_numpy(exec_, b)
+    dc = gko.matrix.Dense.from_numpy(exec_, c0)
+    M.apply(db, dc)
+    assert np.array_equal(dc.to_numpy(), ora.csr_spmv(rp, ci, va, b))
+    dc = gko.matrix.Dense.from_numpy(exec_, c0)
+    M.apply(gko.matrix.Dense.scalar(exec_, 1.25), db, gko.matrix.Dense.scalar(exec_, -0.5), dc)
+    assert np.array_equal(dc.to_numpy(), ora.csr_spmv(rp, ci, va, b, 1.25, -0.5, c0))
