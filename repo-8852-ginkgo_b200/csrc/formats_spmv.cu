@@ -15,9 +15,10 @@
 // Multi-RHS (SpMM): spmm.cuh (warp tiles walked row by row, lane = RHS column).
 //
 // COO (accumulating spmv2, row-sorted): nnz are split evenly over CTAs and threads;
-// products are staged coalesced into shared memory, each thread reduces its run of
-// entries, row pieces are stitched in thread order inside the CTA and per-CTA carries
-// by a small fix-up kernel.  No atomics (the reference's coo kernel uses atomic_add:
+// products are staged coalesced into shared memory, each thread reduces its 9 entries in
+// registers, row pieces are stitched in thread order inside the CTA, row sums leave the CTA
+// as one coalesced read-modify-write of c, per-CTA carries by a small fix-up kernel.  No
+// atomics (the reference's coo kernel uses atomic_add:
 // common/cuda_hip/matrix/coo_kernels.hpp.inc:54-218), deterministic.
 //
 // Algorithmic bytes: ELL n*w*(V+I) + (n_cols+n)*k*V;
@@ -141,126 +142,142 @@ int strided_launch(cudaStream_t s, int64_t n_rows, Fmt fmt, const I* cols, const
 // ---------------------------------------------------------------------------
 // COO  c += [alpha] A b   (row-sorted entries)
 // ---------------------------------------------------------------------------
-constexpr int kCooThreads = 128;
-constexpr int kCooItems = 8;
+constexpr int kCooThreads = 256;
+constexpr int kCooItems = 9;   // odd: the per-thread windows are bank-conflict free
 constexpr int kCooTile = kCooThreads * kCooItems;
 
+// Row-sorted COO, accumulating (c += A b): a segmented reduction over equal-size tiles of
+// entries, the same scheme as the merge-path CSR kernel (csr_spmv.cu):
+//   1. every thread issues all its (row, col, val) loads, then all its gathers (9 independent
+//      requests in flight), products and rows go to shared memory;
+//   2. thread t reduces its 9 consecutive entries in registers; a segment that starts and
+//      ends inside the window is complete;
+//   3. segments spanning threads are stitched in thread order (left-to-right association);
+//   4. the segment touching the first / last entry of the tile may continue in a neighbouring
+//      tile: exported as carries (2 slots per tile, summed in order by coo_fixup);
+//   5. all other row sums are collected in shared memory (the tile's rows are a contiguous
+//      range when the matrix has no long runs of empty rows) and added to c as one coalesced
+//      read-modify-write; tiles spanning more rows than fit update c directly.
+// No atomics (the reference's kernel uses atomic_add: coo_kernels.hpp.inc:54-218), deterministic.
 template <typename V, typename I, bool Advanced>
 __global__ void __launch_bounds__(kCooThreads)
     coo_spmv2(int64_t nnz, const I* __restrict__ rows, const I* __restrict__ cols, const V* __restrict__ vals,
               const V* __restrict__ b, int64_t b_stride, int64_t j, const V* __restrict__ alpha_p,
               V* __restrict__ c, int64_t c_stride, int64_t* __restrict__ carry_row, V* __restrict__ carry_val)
 {
-    // stride kCooItems+1 keeps the per-thread sequential walks bank-conflict free
-    __shared__ V s_prod[kCooThreads * (kCooItems + 1)];
-    __shared__ I s_row[kCooThreads * (kCooItems + 1)];
-    __shared__ I s_first_row[kCooThreads], s_last_row[kCooThreads];
-    __shared__ V s_first_sum[kCooThreads], s_last_sum[kCooThreads];
-    __shared__ bool s_single[kCooThreads];
+    __shared__ V s_prod[kCooTile];
+    __shared__ I s_row[kCooTile];
+    __shared__ unsigned char s_flag[kCooTile];   // row (relative to the tile's first row) received a sum
+    __shared__ V s_lead[kCooThreads];            // sum of a thread's entries before its first head
+    __shared__ bool s_has[kCooThreads];          // the thread's window contains a head
 
     const int tid = threadIdx.x;
     const int64_t k0 = static_cast<int64_t>(blockIdx.x) * kCooTile;
     const int len = static_cast<int>(min(static_cast<int64_t>(kCooTile), nnz - k0));
     V alpha = V(1);
     if (Advanced) alpha = *alpha_p;
-    for (int k = tid; k < len; k += kCooThreads) {
-        const V v = vals[k0 + k];
-        const V xv = ldg(b + static_cast<int64_t>(cols[k0 + k]) * b_stride + j);
-        const int pos = k + k / kCooItems;
-        s_prod[pos] = Advanced ? mul_rn(mul_rn(alpha, v), xv) : mul_rn(v, xv);
-        s_row[pos] = rows[k0 + k];
+    {
+        V v[kCooItems], xv[kCooItems];
+        I col[kCooItems], row[kCooItems];
+#pragma unroll
+        for (int u = 0; u < kCooItems; ++u) {
+            const int k = tid + u * kCooThreads;
+            const bool in = k < len;
+            col[u] = in ? cols[k0 + k] : I(0);
+            v[u] = in ? vals[k0 + k] : V(0);
+            row[u] = in ? rows[k0 + k] : I(-1);
+        }
+#pragma unroll
+        for (int u = 0; u < kCooItems; ++u) xv[u] = ldg(b + static_cast<int64_t>(col[u]) * b_stride + j);
+#pragma unroll
+        for (int u = 0; u < kCooItems; ++u) {
+            const int k = tid + u * kCooThreads;
+            s_prod[k] = k < len ? (Advanced ? mul_rn(mul_rn(alpha, v[u]), xv[u]) : mul_rn(v[u], xv[u])) : V(0);
+            s_row[k] = row[u];
+            s_flag[k] = 0;
+        }
     }
     __syncthreads();
-    // thread t owns entries [t*kCooItems, ...): sequential, in storage order.
-    // Rows that start AND end inside the thread's run are complete: added to c directly
-    // (no other thread touches them).  The first and last row of the run may continue
-    // in neighbouring threads: kept as (row, sum) pieces.
-    const int begin = tid * kCooItems, end = min(begin + kCooItems, len);
-    I first_row = I(-1), last_row = I(-1);
-    V first_sum = V(0), last_sum = V(0);
-    bool single = true;
-    if (begin < end) {
-        const int base = begin + tid;  // padded position of entry `begin`
-        I cur = s_row[base];
-        V sum = s_prod[base];
-        first_row = cur;
-        for (int k = 1; k < end - begin; ++k) {
-            const I r = s_row[base + k];
-            const V p = s_prod[base + k];
-            if (r == cur) {
-                sum = add_rn(sum, p);
-            } else {
-                if (single) {
-                    first_sum = sum;
-                    single = false;
-                } else {
-                    c[static_cast<int64_t>(cur) * c_stride + j] = add_rn(c[static_cast<int64_t>(cur) * c_stride + j], sum);
-                }
-                cur = r;
-                sum = p;
-            }
-        }
-        last_row = cur;
-        last_sum = sum;
-        if (single) first_sum = sum;
+    const I row_first = s_row[0], row_last = s_row[len - 1];
+    // rows of the tile relative to row_first fit the shared result array?
+    const bool dense = static_cast<int64_t>(row_last) - static_cast<int64_t>(row_first) < kCooTile;
+    V p[kCooItems];
+    I r[kCooItems];
+    const int begin = tid * kCooItems;
+#pragma unroll
+    for (int u = 0; u < kCooItems; ++u) {
+        p[u] = s_prod[begin + u];
+        r[u] = s_row[begin + u];
     }
-    s_first_row[tid] = first_row;
-    s_last_row[tid] = last_row;
-    s_first_sum[tid] = first_sum;
-    s_last_sum[tid] = last_sum;
-    s_single[tid] = single;
-    __syncthreads();
-    // Stitch: a "piece list" in thread order: for each thread, its first piece and (if
-    // not single) its last piece.  The leader of each run of equal rows adds the run in
-    // order.  Runs touching the tile's first or last entry are exported as carries
-    // (the neighbouring tiles may continue the same row); the others go to c.
-    if (begin < end) {
-        // does my first piece start a run?  (previous piece = last piece of thread tid-1)
-        const bool starts = tid == 0 || s_last_row[tid - 1] != first_row;
-        if (starts) {
-            V run = first_sum;
-            bool open = single;  // run continues into following threads only if I am a single-row thread
-            int t = tid + 1;
-            while (open && t < kCooThreads && s_first_row[t] == first_row) {
-                run = add_rn(run, s_first_sum[t]);
-                open = s_single[t];
-                ++t;
-            }
-            const bool touches_begin = tid == 0;
-            const bool touches_end = open && (t >= kCooThreads || s_first_row[t] == I(-1));
-            if (touches_begin) {
-                carry_row[2 * blockIdx.x] = first_row;
-                carry_val[2 * blockIdx.x] = run;
-                if (touches_end) {  // the whole tile is one row: second slot empty
-                    carry_row[2 * blockIdx.x + 1] = -1;
-                    carry_val[2 * blockIdx.x + 1] = V(0);
-                }
-            } else if (touches_end) {
-                carry_row[2 * blockIdx.x + 1] = first_row;
-                carry_val[2 * blockIdx.x + 1] = run;
-            } else {
-                c[static_cast<int64_t>(first_row) * c_stride + j] =
-                    add_rn(c[static_cast<int64_t>(first_row) * c_stride + j], run);
-            }
+    const I prev_row = tid > 0 ? s_row[begin - 1] : I(-1);
+    __syncthreads();   // s_prod is reused for the row results from here on
+    V* s_out = s_prod;
+    if (tid == 0) {
+        carry_row[2 * blockIdx.x] = carry_row[2 * blockIdx.x + 1] = -1;
+        carry_val[2 * blockIdx.x] = carry_val[2 * blockIdx.x + 1] = V(0);
+    }
+    // a finished row sum: exported if it touches the tile's first entry, otherwise collected
+    auto deliver = [&](I row, V sum, bool first_seg, bool reaches_end) {
+        if (first_seg) {
+            carry_row[2 * blockIdx.x] = row;
+            carry_val[2 * blockIdx.x] = sum;
+        } else if (reaches_end) {
+            carry_row[2 * blockIdx.x + 1] = row;
+            carry_val[2 * blockIdx.x + 1] = sum;
+        } else if (dense) {
+            s_out[row - row_first] = sum;
+            s_flag[row - row_first] = 1;
+        } else {
+            c[static_cast<int64_t>(row) * c_stride + j] = add_rn(c[static_cast<int64_t>(row) * c_stride + j], sum);
         }
-        if (!single) {
-            // my last piece always starts a run (its row differs from my previous rows)
-            V run = last_sum;
-            bool open = true;
-            int t = tid + 1;
-            while (open && t < kCooThreads && s_first_row[t] == last_row) {
-                run = add_rn(run, s_first_sum[t]);
-                open = s_single[t];
-                ++t;
-            }
-            const bool touches_end = open && (t >= kCooThreads || s_first_row[t] == I(-1));
-            if (touches_end) {
-                carry_row[2 * blockIdx.x + 1] = last_row;
-                carry_val[2 * blockIdx.x + 1] = run;
-            } else {
-                c[static_cast<int64_t>(last_row) * c_stride + j] =
-                    add_rn(c[static_cast<int64_t>(last_row) * c_stride + j], run);
-            }
+    };
+    V lead = V(0), acc = V(0);
+    bool has = false, seg_first = false;
+    I seg_row = I(-1);
+    // (the carry defaults above are ordered before every deliver() of another thread by the
+    // barrier below; thread 0's own in-window deliveries follow them in program order)
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < kCooItems; ++u) {
+        const bool valid = begin + u < len;
+        const bool head = valid && (u == 0 ? (tid == 0 || r[0] != prev_row) : r[u] != r[u - 1]);
+        if (head) {
+            if (!has)
+                lead = acc;
+            else
+                deliver(seg_row, acc, seg_first, false);   // starts and ends inside this window
+            has = true;
+            seg_row = r[u];
+            seg_first = tid == 0 && u == 0;
+            acc = p[u];
+        } else {
+            acc = add_rn(acc, p[u]);   // entries past the end of the tile are zeros
+        }
+    }
+    if (!has) lead = acc;
+    s_lead[tid] = lead;
+    s_has[tid] = has;
+    __syncthreads();
+    if (has) {
+        // leader of the row of my last head: my trailing sum + the leading sums of the following
+        // threads up to and including the next thread with a head
+        V run = acc;
+        int t = tid + 1;
+        bool ended = false;
+        while (t < kCooThreads && !ended) {
+            run = add_rn(run, s_lead[t]);
+            ended = s_has[t];
+            ++t;
+        }
+        deliver(seg_row, run, seg_first, !ended);
+    }
+    if (!dense) return;
+    __syncthreads();
+    const int span = static_cast<int>(row_last - row_first) + 1;
+    for (int q = tid; q < span; q += kCooThreads) {
+        if (s_flag[q]) {
+            const int64_t at = (static_cast<int64_t>(row_first) + q) * c_stride + j;
+            c[at] = add_rn(c[at], s_out[q]);
         }
     }
 }
@@ -300,7 +317,6 @@ int coo_spmv2_launch(cudaStream_t s, int64_t n_rows, int64_t nnz, const I* rows,
     int64_t* carry_row = reinterpret_cast<int64_t*>(workspace);
     V* carry_val = reinterpret_cast<V*>(carry_row + 2 * n_tiles);
     for (int64_t j = 0; j < nrhs; ++j) {
-        GKOB200_CUDA(cudaMemsetAsync(carry_row, 0xff, static_cast<size_t>(2 * n_tiles) * sizeof(int64_t), s));
         if (alpha)
             coo_spmv2<V, I, true><<<static_cast<unsigned>(n_tiles), kCooThreads, 0, s>>>(
                 nnz, rows, cols, vals, b, b_stride, j, alpha, c, c_stride, carry_row, carry_val);
