@@ -157,6 +157,10 @@ int gkob200_dist_comm_create(const void* id128, int rank, int size, gkob200_dist
 int gkob200_dist_comm_destroy(gkob200_dist_comm* comm);
 int gkob200_dist_comm_rank(const gkob200_dist_comm* comm);
 int gkob200_dist_comm_size(const gkob200_dist_comm* comm);
+/* 1 when the scalar all-reduces of this communicator run over peer memory (CUDA IPC over
+ * NVLink, one small kernel) instead of ncclAllReduce: every rank on its own GPU and every peer
+ * mappable; GKOB200_P2P=0 in the environment forces NCCL. */
+int gkob200_dist_comm_uses_p2p(const gkob200_dist_comm* comm);
 /* [ref: mpi::communicator::all_reduce / all_to_all / all_to_all_v,
  *  call sites core/distributed/vector.cpp:328-440, matrix.cpp:204-221]; device buffers */
 int gkob200_dist_allreduce_sum_f64(gkob200_dist_comm* comm, void* stream, double* buf, int64_t count);

@@ -158,6 +158,7 @@ def declare(lib):
     d("gkob200_dist_comm_destroy", [vp])
     d("gkob200_dist_comm_rank", [vp])
     d("gkob200_dist_comm_size", [vp])
+    d("gkob200_dist_comm_uses_p2p", [vp])
     d("gkob200_dist_allreduce_sum_f64", [vp, vp, vp, i64])
     d("gkob200_dist_allreduce_sum_f32", [vp, vp, vp, i64])
     d("gkob200_dist_alltoall_i64", [vp, vp, vp, vp, i64])

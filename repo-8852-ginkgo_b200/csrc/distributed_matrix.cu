@@ -18,6 +18,7 @@
 #include <cstring>
 #include <vector>
 
+#include "p2p.cuh"
 #include "solver_common.cuh"
 
 #define GKOB200_NCCL(call)                                        \
@@ -26,10 +27,18 @@
         if (r__ != ncclSuccess) return 1000 + static_cast<int>(r__); \
     } while (0)
 
+using gkob200::P2pDev;
+using gkob200::kP2pMaxRanks;
+using gkob200::kP2pBlockBytes;
+using gkob200::kP2pErrorOff;
+
 struct gkob200_dist_comm {
     ncclComm_t comm = nullptr;
     int rank = 0, size = 1;
     cudaStream_t comm_stream = nullptr;
+    bool p2p = false;
+    P2pDev p2p_dev{};
+    P2pDev* p2p_dev_ptr = nullptr;   // device copy (for kernels that get it through a pointer)
 };
 
 struct gkob200_dist_matrix {
@@ -42,6 +51,7 @@ struct gkob200_dist_matrix {
     int64_t buf_nrhs = 0;
     cudaEvent_t packed = nullptr, received = nullptr;
     int64_t launches = 0;
+    bool exchanged = false;   // the last apply all-reduced its fused dot inside the non-local kernel
 };
 
 namespace gkob200 {
@@ -53,6 +63,99 @@ template <>
 ncclDataType_t nccl_type<double>() { return ncclDouble; }
 template <>
 ncclDataType_t nccl_type<float>() { return ncclFloat; }
+
+// stand-alone all-reduce (ranks whose producing kernel cannot do the exchange itself)
+template <typename V>
+__global__ void p2p_allreduce_kernel(P2pDev pr, V* buf, int count, const int* skip)
+{
+    // `skip`: the solver's stopped flag — identical on every rank (it derives from all-reduced
+    // values), and the fused exchanges inside the solver kernels honour it too
+    if (skip && *skip) return;
+    peer_allreduce(pr, buf, count);
+}
+
+// Exchanges IPC handles + device UUIDs through the NCCL communicator and maps the peers'
+// blocks.  Used only if EVERY rank could map every peer and all ranks sit on distinct GPUs
+// (two spinning ranks time-slicing one GPU would wait for each other).
+int p2p_setup(gkob200_dist_comm* c)
+{
+    const char* env = getenv("GKOB200_P2P");
+    if ((env && env[0] == '0') || c->size > kP2pMaxRanks) return 0;
+    struct Record {
+        cudaIpcMemHandle_t handle;
+        char uuid[16];
+        char pad[128 - sizeof(cudaIpcMemHandle_t) - 16];
+    };
+    static_assert(sizeof(Record) == 128, "record size");
+    unsigned char* local = nullptr;
+    GKOB200_CUDA(cudaMalloc(&local, kP2pBlockBytes));
+    GKOB200_CUDA(cudaMemset(local, 0, kP2pBlockBytes));
+    Record mine{};
+    int dev = 0;
+    GKOB200_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    GKOB200_CUDA(cudaGetDeviceProperties(&prop, dev));
+    memcpy(mine.uuid, &prop.uuid, 16);
+    int ok = cudaIpcGetMemHandle(&mine.handle, local) == cudaSuccess ? 1 : 0;
+    cudaGetLastError();
+    unsigned char* d_rec = nullptr;
+    GKOB200_CUDA(cudaMalloc(&d_rec, sizeof(Record) * (c->size + 1)));
+    GKOB200_CUDA(cudaMemcpy(d_rec, &mine, sizeof(Record), cudaMemcpyHostToDevice));
+    GKOB200_NCCL(ncclAllGather(d_rec, d_rec + sizeof(Record), sizeof(Record), ncclChar, c->comm, c->comm_stream));
+    GKOB200_CUDA(cudaStreamSynchronize(c->comm_stream));
+    std::vector<Record> all(c->size);
+    GKOB200_CUDA(cudaMemcpy(all.data(), d_rec + sizeof(Record), sizeof(Record) * c->size, cudaMemcpyDeviceToHost));
+    c->p2p_dev.rank = c->rank;
+    c->p2p_dev.size = c->size;
+    for (int r = 0; r < c->size && ok; ++r) {
+        for (int q = 0; q < r; ++q)
+            if (memcmp(all[r].uuid, all[q].uuid, 16) == 0) ok = 0;   // two ranks on one GPU
+        if (r == c->rank) {
+            c->p2p_dev.block[r] = local;
+        } else if (ok) {
+            void* ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                ok = 0;
+            }
+            c->p2p_dev.block[r] = static_cast<unsigned char*>(ptr);
+        }
+    }
+    // all or nobody
+    int* d_ok = reinterpret_cast<int*>(d_rec);
+    GKOB200_CUDA(cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice));
+    GKOB200_NCCL(ncclAllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, c->comm, c->comm_stream));
+    GKOB200_CUDA(cudaStreamSynchronize(c->comm_stream));
+    GKOB200_CUDA(cudaMemcpy(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(d_rec);
+    c->p2p = ok != 0;
+    if (c->p2p) {
+        GKOB200_CUDA(cudaMalloc(&c->p2p_dev_ptr, sizeof(P2pDev)));
+        GKOB200_CUDA(cudaMemcpy(c->p2p_dev_ptr, &c->p2p_dev, sizeof(P2pDev), cudaMemcpyHostToDevice));
+    }
+    if (!c->p2p) {
+        for (int r = 0; r < c->size; ++r)
+            if (r != c->rank && c->p2p_dev.block[r]) cudaIpcCloseMemHandle(c->p2p_dev.block[r]);
+        cudaGetLastError();
+        cudaFree(local);
+        c->p2p_dev = P2pDev{};
+    }
+    return 0;
+}
+
+// in-place sum of `count` scalars over all ranks, on stream s
+template <typename V>
+int comm_allreduce(gkob200_dist_comm* c, cudaStream_t s, V* buf, size_t count, const int* skip = nullptr)
+{
+    if (!c || c->size == 1 || count == 0) return 0;
+    if (c->p2p && count <= 4) {
+        p2p_allreduce_kernel<V><<<1, 1, 0, s>>>(c->p2p_dev, buf, static_cast<int>(count), skip);
+        GKOB200_CHECK_LAUNCH();
+        return 0;
+    }
+    GKOB200_NCCL(ncclAllReduce(buf, buf, count, nccl_type<V>(), ncclSum, c->comm, s));
+    return 0;
+}
 
 template <typename V>
 __global__ void __launch_bounds__(256)
@@ -136,7 +239,10 @@ int dist_apply(gkob200_dist_matrix* m, cudaStream_t s, const V* b, int64_t bs, i
             fl.out = nullptr;
         }
         if (split && fn.out) fn.out = fn.out + 1;
+        fl.p2p = nullptr;   // only the last kernel of the apply may exchange
+        if (!(split && fn.out)) fn.p2p = nullptr;
     }
+    m->exchanged = fusion && nl && fn.p2p != nullptr;
     if ((rc = matrix_apply<V>(s, m->local, b, bs, nrhs, alpha, beta, x, xs, fusion ? &fl : nullptr))) return rc;
     ++m->launches;
     if (has_halo) GKOB200_CUDA(cudaStreamWaitEvent(s, m->received, 0));
@@ -168,6 +274,7 @@ struct DistCgParams {
     V factor;
     int64_t max_iters;
     void* ws;
+    const P2pDev* p2p;   // non-null: the reduction finaliser all-reduces over peer memory itself
 };
 
 // x += t p ; r -= t q ; z = M^-1 r ; partial sums (r.z, r.r) -> sc[D_RED0..1]
@@ -199,10 +306,20 @@ __global__ void __launch_bounds__(256) dist_cg_update(DistCgParams<V> P)
         acc[0] += ri * zi;
         acc[1] += ri * ri;
     }
-    V* sc = P.sc;
-    grid_reduce<2>(acc, ws_partials<V>(P.ws), ws_ticket(P.ws), [sc](V(&tot)[2]) {
-        sc[D_RED0] = tot[0];
-        sc[D_RED1] = tot[1];
+    DistCgParams<V> Q = P;
+    grid_reduce<2>(acc, ws_partials<V>(P.ws), ws_ticket(P.ws), [Q](V(&tot)[2]) {
+        Q.sc[D_RED0] = tot[0];
+        Q.sc[D_RED1] = tot[1];
+        if (Q.p2p) {
+            // all-reduce over peer memory + rho bookkeeping + criterion, all in this finaliser
+            // (otherwise: ncclAllReduce + dist_cg_scalars, two more launches)
+            peer_allreduce(*Q.p2p, Q.sc + D_RED0, 2);
+            if (!First) Q.sc[D_PREV_RHO] = Q.sc[D_RHO];
+            Q.sc[D_RHO] = Q.sc[D_RED0];
+            Q.sc[D_TAU] = sqrt_rn(Q.sc[D_RED1]);
+            criterion_check(Q.st, 1, Q.sc + D_TAU, Q.sc + D_ORIG_TAU, Q.factor, Q.max_iters, true, Q.stop_status,
+                            Q.hist, true);
+        }
     });
 }
 
@@ -285,6 +402,7 @@ struct DistCgSolver : SolverBase<V> {
         P.factor = static_cast<V>(stop.reduction_factor);
         P.max_iters = stop.max_iters;
         P.ws = bigws.p;
+        P.p2p = (dm->comm && dm->comm->p2p) ? dm->comm->p2p_dev_ptr : nullptr;
         return P;
     }
 
@@ -292,9 +410,8 @@ struct DistCgSolver : SolverBase<V> {
     {
         gkob200_dist_comm* c = dm->comm;
         if (!c || c->size == 1) return 0;
-        GKOB200_NCCL(ncclAllReduce(buf, buf, count, nccl_type<V>(), ncclSum, c->comm, s));
         ++launch_count;
-        return 0;
+        return comm_allreduce<V>(c, s, buf, count, &this->st()->stopped);
     }
 
     template <bool First>
@@ -307,10 +424,12 @@ struct DistCgSolver : SolverBase<V> {
         else
             dist_cg_update<V, 1, First><<<grid, 256, 0, s>>>(P);
         GKOB200_CHECK_LAUNCH();
+        ++launch_count;
+        if (P.p2p) return 0;   // exchange + scalars happened in the kernel's finaliser
         int rc = allreduce(s, P.sc + D_RED0, 2);
         if (rc) return rc;
         dist_cg_scalars<V, First><<<1, 1, 0, s>>>(P);
-        launch_count += 2;
+        ++launch_count;
         GKOB200_CHECK_LAUNCH();
         return 0;
     }
@@ -364,13 +483,27 @@ struct DistCgSolver : SolverBase<V> {
             fu.out = P.sc + D_BETA;
             fu.ws = bigws.p;
             fu.ws_blocks = ws_blocks;
+            if (P.p2p) {
+                fu.p2p = P.p2p;
+                fu.p2p_buf = P.sc + D_BETA;
+                fu.p2p_count = 2;
+            }
             if ((rc = dist_apply<V>(dm, s, P.p, 1, 1, nullptr, nullptr, P.q, 1, &fu))) return rc;
-            if ((rc = allreduce(s, P.sc + D_BETA, 2))) return rc;
+            // (a rank without a non-local block all-reduces with the stand-alone kernel)
+            if (!dm->exchanged && (rc = allreduce(s, P.sc + D_BETA, 2))) return rc;
             if ((rc = update<false>(s, x))) return rc;
             ++it;
         }
         launch_count += dm->launches;
-        return this->finish(s);
+        if ((rc = this->finish(s))) return rc;
+        if (dm->comm && dm->comm->p2p) {
+            // a peer that never showed up in a peer-memory all-reduce (bounded spin)
+            int err = 0;
+            GKOB200_CUDA(cudaMemcpy(&err, dm->comm->p2p_dev.block[dm->comm->rank] + kP2pErrorOff, sizeof(int),
+                                    cudaMemcpyDeviceToHost));
+            if (err) return 2000;
+        }
+        return 0;
     }
 };
 
@@ -415,13 +548,30 @@ int gkob200_dist_comm_create(const void* id128, int rank, int size, gkob200_dist
         delete c;
         return static_cast<int>(e);
     }
+    if (size > 1) {
+        int rc = p2p_setup(c);
+        if (rc) {
+            delete c;
+            return rc;
+        }
+    }
     *out = c;
     return 0;
 }
 
+/* 1 when scalar all-reduces run over peer memory (CUDA IPC) instead of NCCL */
+int gkob200_dist_comm_uses_p2p(const gkob200_dist_comm* c) { return c && c->p2p ? 1 : 0; }
+
 int gkob200_dist_comm_destroy(gkob200_dist_comm* c)
 {
     if (!c) return 0;
+    if (c->p2p) {
+        cudaDeviceSynchronize();
+        for (int r = 0; r < c->size; ++r)
+            if (r != c->rank && c->p2p_dev.block[r]) cudaIpcCloseMemHandle(c->p2p_dev.block[r]);
+        cudaFree(c->p2p_dev.block[c->rank]);
+        cudaFree(c->p2p_dev_ptr);
+    }
     if (c->comm) ncclCommDestroy(c->comm);
     if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
     delete c;
@@ -435,16 +585,12 @@ int gkob200_dist_comm_size(const gkob200_dist_comm* c) { return c ? c->size : -1
 int gkob200_dist_allreduce_sum_f64(gkob200_dist_comm* c, void* stream, double* buf, int64_t count)
 {
     if (!c || count < 0) return GKOB200_EINVAL;
-    if (c->size == 1 || count == 0) return 0;
-    GKOB200_NCCL(ncclAllReduce(buf, buf, static_cast<size_t>(count), ncclDouble, ncclSum, c->comm, as_stream(stream)));
-    return 0;
+    return comm_allreduce<double>(c, as_stream(stream), buf, static_cast<size_t>(count));
 }
 int gkob200_dist_allreduce_sum_f32(gkob200_dist_comm* c, void* stream, float* buf, int64_t count)
 {
     if (!c || count < 0) return GKOB200_EINVAL;
-    if (c->size == 1 || count == 0) return 0;
-    GKOB200_NCCL(ncclAllReduce(buf, buf, static_cast<size_t>(count), ncclFloat, ncclSum, c->comm, as_stream(stream)));
-    return 0;
+    return comm_allreduce<float>(c, as_stream(stream), buf, static_cast<size_t>(count));
 }
 /* all-to-all of `count` int64 per peer (device buffers): setup exchange of halo sizes */
 int gkob200_dist_alltoall_i64(gkob200_dist_comm* c, void* stream, const int64_t* send, int64_t* recv, int64_t count)

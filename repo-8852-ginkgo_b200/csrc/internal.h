@@ -16,6 +16,11 @@ struct SpmvFusion {
     const V* w = nullptr;
     V* out = nullptr;
     V* out_sq = nullptr;    // optional second fused reduction: sum of result^2 (needs `out`)
+    // optional: the kernel whose finaliser completes `out` also all-reduces p2p_count values at
+    // p2p_buf over peer memory (p2p.cuh; only the row-compressed non-local SpMV implements it)
+    const void* p2p = nullptr;
+    V* p2p_buf = nullptr;
+    int p2p_count = 0;
     void* ws = nullptr;
     int64_t ws_blocks = 0;  // number of per-block partials `ws` has room for
 };

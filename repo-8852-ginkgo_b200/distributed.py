@@ -55,6 +55,11 @@ class Communicator:
         if h and lib is not None:  # lib is None while the interpreter shuts down
             lib.gkob200_dist_comm_destroy(h)
 
+    @property
+    def uses_p2p(self):
+        """scalar all-reduces run over peer memory (CUDA IPC) instead of NCCL"""
+        return bool(lib.gkob200_dist_comm_uses_p2p(self._h))
+
     def all_reduce_sum(self, t):
         fn = lib.gkob200_dist_allreduce_sum_f64 if t.dtype == torch.float64 else lib.gkob200_dist_allreduce_sum_f32
         check(fn(self._h, current_stream(), ptr(t), t.numel()), "all_reduce")

@@ -69,6 +69,7 @@ def solve():
 
 res["cg_iteration_us"] = timed(solve, 3) / iters
 res["launches_per_iteration"] = s.launch_count / iters
+res["p2p_allreduce"] = comm.uses_p2p
 if rank == 0:
     print("BREAKDOWN", world, res, flush=True)
 dist.destroy_process_group()
