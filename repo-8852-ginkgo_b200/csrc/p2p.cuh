@@ -40,11 +40,13 @@ __device__ __forceinline__ void peer_allreduce(const P2pDev& pr, V* buf, int cou
                                (parity * kP2pMaxRanks + pr.rank) * 4;
         for (int c = 0; c < count; ++c) dst[c] = v[c];
     }
+    // ONE system-scope fence orders all the value stores before all the flag stores (a release
+    // store per flag would wait for an NVLink round trip eight times: 25 us instead of 5)
     __threadfence_system();
     for (int r = 0; r < pr.size; ++r) {
         unsigned long long* f = reinterpret_cast<unsigned long long*>(pr.block[r] + kP2pFlagsOff) +
                                 parity * kP2pMaxRanks + pr.rank;
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(e) : "memory");
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(f), "l"(e) : "memory");
     }
     double tot[4] = {0.0, 0.0, 0.0, 0.0};
     for (int r = 0; r < pr.size; ++r) {
