@@ -382,6 +382,42 @@ int64_t gkob200_gen_powerlaw_row_ptrs_i64(int64_t n, uint64_t seed, double lmin,
 int gkob200_gen_powerlaw_fill_f64_i32(int64_t n, uint64_t seed, const int64_t* row_ptrs_host,
                                       int32_t* row_ptrs32_host, int32_t* col_idxs_host, double* values_host);
 
+/* ------------------------------------------------------------------------- *
+ * Matrix assembly on the device (setup path, not the hot loop)
+ * [ref: components::sort_row_major / sum_duplicates / remove_zeros
+ *       core/base/device_matrix_data.cpp, reference/base/device_matrix_data_kernels.cpp:82-172;
+ *       csr::transpose reference/matrix/csr_kernels.cpp:551-587;
+ *       csr::sort_by_column_index reference/matrix/csr_kernels.cpp:969-987]
+ * sort_row_major is a STABLE sort by (row, col) (the reference's std::sort leaves the order of
+ * duplicates unspecified); sum_duplicates / remove_zeros expect what the reference's callers
+ * give them (row-major sorted input for sum_duplicates), write to separate output arrays of
+ * capacity nnz and leave the new entry count in *out_nnz (device memory); duplicates are added
+ * in input order starting from zero, like the reference loop.  Integer outputs bit-exact,
+ * values bit-exact.  Workspaces: gkob200_setup_sort_workspace_bytes for sort_row_major /
+ * transpose / sort_by_column_index, gkob200_setup_compact_workspace_bytes for the other two.
+ * ------------------------------------------------------------------------- */
+size_t gkob200_setup_sort_workspace_bytes(int64_t nnz, int value_bytes, int index_bytes);
+size_t gkob200_setup_compact_workspace_bytes(int64_t nnz);
+#define GKOB200_DECL_SETUP(V, VT, I, IT)                                                                           \
+    int gkob200_coo_sort_row_major_##V##_##I(void* stream, int64_t n_rows, int64_t n_cols, int64_t nnz, IT* rows,   \
+                                             IT* cols, VT* vals, void* ws, size_t ws_bytes);                       \
+    int gkob200_coo_sum_duplicates_##V##_##I(void* stream, int64_t nnz, const IT* rows, const IT* cols,             \
+                                             const VT* vals, IT* out_rows, IT* out_cols, VT* out_vals,              \
+                                             int64_t* out_nnz, void* ws, size_t ws_bytes);                         \
+    int gkob200_coo_remove_zeros_##V##_##I(void* stream, int64_t nnz, const IT* rows, const IT* cols,               \
+                                           const VT* vals, IT* out_rows, IT* out_cols, VT* out_vals,                \
+                                           int64_t* out_nnz, void* ws, size_t ws_bytes);                           \
+    int gkob200_csr_transpose_##V##_##I(void* stream, int64_t n_rows, int64_t n_cols, int64_t nnz,                  \
+                                        const IT* row_ptrs, const IT* col_idxs, const VT* values, IT* out_row_ptrs, \
+                                        IT* out_col_idxs, VT* out_values, void* ws, size_t ws_bytes);              \
+    int gkob200_csr_sort_by_column_index_##V##_##I(void* stream, int64_t n_rows, int64_t n_cols, int64_t nnz,       \
+                                                   const IT* row_ptrs, IT* col_idxs, VT* values, void* ws,          \
+                                                   size_t ws_bytes);
+GKOB200_DECL_SETUP(f64, double, i32, int32_t)
+GKOB200_DECL_SETUP(f32, float, i32, int32_t)
+GKOB200_DECL_SETUP(f64, double, i64, int64_t)
+GKOB200_DECL_SETUP(f32, float, i64, int64_t)
+
 #ifdef __cplusplus
 } /* extern "C" */
 #endif

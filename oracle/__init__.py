@@ -567,3 +567,60 @@ def global_to_local(part, v, p):
 
 def local_to_global(part, v, p, loc):
     v[_local_rows(part, p)] = loc
+
+
+# ---- matrix assembly -------------------------------------------
+SORT, SUM_DUPLICATES, REMOVE_ZEROS = 1, 2, 4
+
+
+def coo_assemble(rows, cols, vals, steps=SORT | SUM_DUPLICATES | REMOVE_ZEROS):
+    """device_matrix_data::{sort_row_major, sum_duplicates, remove_zeros} (plain-C oracle);
+    returns new (rows, cols, vals)."""
+    r, c, v = rows.copy(), cols.copy(), vals.copy()
+    V, I = _v(v.dtype), _i(r.dtype)
+    n = len(v)
+    L = lib()
+    if steps & SORT:
+        getattr(L, f"oracle_coo_sort_row_major_{I}_{V}")(i64(n), P(r), P(c), P(v))
+    if steps & SUM_DUPLICATES:
+        fn = getattr(L, f"oracle_coo_sum_duplicates_{I}_{V}")
+        fn.restype = i64
+        n = fn(i64(n), P(r), P(c), P(v))
+    if steps & REMOVE_ZEROS:
+        fn = getattr(L, f"oracle_coo_remove_zeros_{I}_{V}")
+        fn.restype = i64
+        n = fn(i64(n), P(r), P(c), P(v))
+    return r[:n].copy(), c[:n].copy(), v[:n].copy()
+
+
+def csr_transpose(n_rows, n_cols, rp, ci, va):
+    out_rp = np.zeros(n_cols + 1, dtype=rp.dtype)
+    out_ci, out_va = np.zeros_like(ci), np.zeros_like(va)
+    getattr(lib(), f"oracle_csr_transpose_{_i(rp.dtype)}_{_v(va.dtype)}")(i64(n_rows), i64(n_cols), P(rp), P(ci), P(va),
+                                                                          P(out_rp), P(out_ci), P(out_va))
+    return out_rp, out_ci, out_va
+
+
+def csr_sort_by_column_index(rp, ci, va):
+    c, v = ci.copy(), va.copy()
+    getattr(lib(), f"oracle_csr_sort_by_column_index_{_i(rp.dtype)}_{_v(va.dtype)}")(i64(len(rp) - 1), P(rp), P(c), P(v))
+    return c, v
+
+
+def ref_assemble(n_rows, n_cols, rows, cols, vals, steps=SORT | SUM_DUPLICATES | REMOVE_ZEROS):
+    """The same steps on the real reference executor; also returns the row_ptrs Csr::read builds."""
+    r, c, v = rows.copy(), cols.copy(), vals.copy()
+    rp = np.zeros(n_rows + 1, dtype=r.dtype)
+    fn = getattr(ref(), f"ref_assemble_{_v(v.dtype)}_{_i(r.dtype)}")
+    fn.restype = i64
+    n = fn(int(steps), i64(n_rows), i64(n_cols), i64(len(v)), P(r), P(c), P(v), P(rp))
+    return r[:n].copy(), c[:n].copy(), v[:n].copy(), rp
+
+
+def ref_csr_op(op, n_rows, n_cols, rp, ci, va):
+    """op 0: transpose, 1: sort_by_column_index on the real reference executor."""
+    out_rp = np.zeros((n_cols if op == 0 else n_rows) + 1, dtype=rp.dtype)
+    out_ci, out_va = np.zeros_like(ci), np.zeros_like(va)
+    getattr(ref(), f"ref_csr_op_{_v(va.dtype)}_{_i(rp.dtype)}")(int(op), i64(n_rows), i64(n_cols), i64(len(ci)), P(rp),
+                                                                P(ci), P(va), P(out_rp), P(out_ci), P(out_va))
+    return out_rp, out_ci, out_va

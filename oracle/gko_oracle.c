@@ -94,6 +94,7 @@ void oracle_hybrid_compute_coo_row_ptrs(const uint64_t* row_nnz, int64_t n, uint
 #define SQRT sqrt
 #define FABS fabs
 #include "oracle_kernels.inc"
+#include "oracle_setup.inc"
 #undef V
 #undef SFX
 #undef SQRT
@@ -104,6 +105,7 @@ void oracle_hybrid_compute_coo_row_ptrs(const uint64_t* row_nnz, int64_t n, uint
 #define SQRT sqrtf
 #define FABS fabsf
 #include "oracle_kernels.inc"
+#include "oracle_setup.inc"
 #undef V
 #undef SFX
 #undef SQRT

@@ -390,6 +390,54 @@ int dist_build_impl(int mode, int num_parts, int64_t global_size, const int64_t*
     }
 }
 
+// device_matrix_data assembly on the reference executor: sort_row_major -> sum_duplicates ->
+// remove_zeros (each step optional), then the Csr the reference would read from it.
+template <typename V, typename I>
+int64_t assemble_impl(int steps, int64_t n_rows, int64_t n_cols, int64_t nnz, I* rows, I* cols, V* vals, I* out_rp)
+{
+    auto exec = gko::ReferenceExecutor::create();
+    gko::device_matrix_data<V, I> data{exec, gko::dim<2>(n_rows, n_cols), static_cast<gko::size_type>(nnz)};
+    std::memcpy(data.get_row_idxs(), rows, nnz * sizeof(I));
+    std::memcpy(data.get_col_idxs(), cols, nnz * sizeof(I));
+    std::memcpy(data.get_values(), vals, nnz * sizeof(V));
+    if (steps & 1) data.sort_row_major();
+    if (steps & 2) data.sum_duplicates();
+    if (steps & 4) data.remove_zeros();
+    const int64_t m = static_cast<int64_t>(data.get_num_elems());
+    std::memcpy(rows, data.get_const_row_idxs(), m * sizeof(I));
+    std::memcpy(cols, data.get_const_col_idxs(), m * sizeof(I));
+    std::memcpy(vals, data.get_const_values(), m * sizeof(V));
+    if (out_rp) {
+        auto csr = gko::matrix::Csr<V, I>::create(exec);
+        csr->read(data);
+        std::memcpy(out_rp, csr->get_const_row_ptrs(), (n_rows + 1) * sizeof(I));
+    }
+    return m;
+}
+
+// op 0: transpose (out arrays of the transposed matrix), op 1: sort_by_column_index (in place:
+// out_ci / out_va receive the sorted arrays, out_rp a copy of rp)
+template <typename V, typename I>
+int csr_op_impl(int op, int64_t n_rows, int64_t n_cols, int64_t nnz, const I* rp, const I* ci, const V* va, I* out_rp,
+                I* out_ci, V* out_va)
+{
+    auto exec = gko::ReferenceExecutor::create();
+    auto A = csr_view<V, I>(exec, n_rows, n_cols, nnz, rp, ci, va);
+    if (op == 0) {
+        auto T = gko::as<gko::matrix::Csr<V, I>>(A->transpose());
+        std::memcpy(out_rp, T->get_const_row_ptrs(), (n_cols + 1) * sizeof(I));
+        std::memcpy(out_ci, T->get_const_col_idxs(), nnz * sizeof(I));
+        std::memcpy(out_va, T->get_const_values(), nnz * sizeof(V));
+    } else {
+        auto B = A->clone();
+        B->sort_by_column_index();
+        std::memcpy(out_rp, B->get_const_row_ptrs(), (n_rows + 1) * sizeof(I));
+        std::memcpy(out_ci, B->get_const_col_idxs(), nnz * sizeof(I));
+        std::memcpy(out_va, B->get_const_values(), nnz * sizeof(V));
+    }
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -447,6 +495,16 @@ int64_t ref_jacobi_generate_f32_i32(int64_t n, int64_t nnz, const int32_t* rp, c
 {
     return jacobi_impl<float, int32_t>(n, nnz, rp, ci, va, max_block_size, meta, block_ptrs, blocks, cap);
 }
+#define REF_SETUP(V, VT, I, IT)                                                                                  \
+    int64_t ref_assemble_##V##_##I(int steps, int64_t n_rows, int64_t n_cols, int64_t nnz, IT* rows, IT* cols,   \
+                                   VT* vals, IT* out_rp)                                                         \
+    { return assemble_impl<VT, IT>(steps, n_rows, n_cols, nnz, rows, cols, vals, out_rp); }                      \
+    int ref_csr_op_##V##_##I(int op, int64_t n_rows, int64_t n_cols, int64_t nnz, const IT* rp, const IT* ci,    \
+                             const VT* va, IT* out_rp, IT* out_ci, VT* out_va)                                   \
+    { return csr_op_impl<VT, IT>(op, n_rows, n_cols, nnz, rp, ci, va, out_rp, out_ci, out_va); }
+REF_SETUP(f64, double, i32, int32_t)
+REF_SETUP(f32, float, i32, int32_t)
+REF_SETUP(f64, double, i64, int64_t)
 REF_CONVERT(f64, double, i32, int32_t)
 REF_CONVERT(f32, float, i32, int32_t)
 REF_CONVERT(f64, double, i64, int64_t)

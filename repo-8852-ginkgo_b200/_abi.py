@@ -134,6 +134,16 @@ def declare(lib):
         d(f"gkob200_jacobi_block_apply_{V}", [vp, i64, vp, vp, i64, i64, C.c_int, i64, i64, vp, vp, i64, vp, vp, i64])
     d("gkob200_jacobi_find_blocks_workspace_bytes", [i64], sz)
     d("gkob200_jacobi_find_blocks_i32", [vp, i64, vp, vp, i32, vp, vp, vp, sz])
+    # matrix assembly (setup path)
+    d("gkob200_setup_sort_workspace_bytes", [i64, C.c_int, C.c_int], sz)
+    d("gkob200_setup_compact_workspace_bytes", [i64], sz)
+    for V in VT:
+        for I in ("i32", "i64"):
+            d(f"gkob200_coo_sort_row_major_{V}_{I}", [vp, i64, i64, i64, vp, vp, vp, vp, sz])
+            d(f"gkob200_coo_sum_duplicates_{V}_{I}", [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, sz])
+            d(f"gkob200_coo_remove_zeros_{V}_{I}", [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, sz])
+            d(f"gkob200_csr_transpose_{V}_{I}", [vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, sz])
+            d(f"gkob200_csr_sort_by_column_index_{V}_{I}", [vp, i64, i64, i64, vp, vp, vp, vp, sz])
     # generators (host)
     d("gkob200_gen_stencil_nnz", [C.c_int, i64, i64, i64, i64, i64], i64)
     for V in VT:
