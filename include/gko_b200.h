@@ -418,6 +418,31 @@ GKOB200_DECL_SETUP(f32, float, i32, int32_t)
 GKOB200_DECL_SETUP(f64, double, i64, int64_t)
 GKOB200_DECL_SETUP(f32, float, i64, int64_t)
 
+/* ------------------------------------------------------------------------- *
+ * Wire / disk formats of the callers (host code, no GPU needed)
+ * [ref: core/base/mtx_io.cpp — read (MatrixMarket text) :77-103, header grammar :690-722,
+ *  storage modifiers :293-463, layouts :509-655, GINKGO binary format :776-958,
+ *  read_generic_raw :911-925]
+ * gkob200_mtx_read_open parses a whole file (text or binary, chosen by its first byte like
+ * read_generic_raw) into row-major sorted triplets; _copy_ converts them into caller-owned HOST
+ * arrays of nnz entries; complex files are rejected (real value types only), indices that do
+ * not fit the requested index type are rejected.  Errors return GKOB200_EINVAL and leave a
+ * message in gkob200_mtx_last_error() (thread-local), the reference's stream-error texts.
+ * gkob200_mtx_write_*: format 0 = "%%MatrixMarket matrix coordinate real general" (precision <= 0:
+ * 6 significant digits, what the reference's ostream default gives), 1 = GINKGO binary.
+ * ------------------------------------------------------------------------- */
+const char* gkob200_mtx_last_error(void);
+int gkob200_mtx_read_open(const char* path, void** handle, int64_t* n_rows, int64_t* n_cols, int64_t* nnz);
+int gkob200_mtx_read_close(void* handle);
+#define GKOB200_DECL_MTX(V, VT, I, IT)                                                                             \
+    int gkob200_mtx_read_copy_##V##_##I(void* handle, IT* rows, IT* cols, VT* vals);                                \
+    int gkob200_mtx_write_##V##_##I(const char* path, int format, int precision, int64_t n_rows, int64_t n_cols,    \
+                                    int64_t nnz, const IT* rows, const IT* cols, const VT* vals);
+GKOB200_DECL_MTX(f64, double, i32, int32_t)
+GKOB200_DECL_MTX(f32, float, i32, int32_t)
+GKOB200_DECL_MTX(f64, double, i64, int64_t)
+GKOB200_DECL_MTX(f32, float, i64, int64_t)
+
 #ifdef __cplusplus
 } /* extern "C" */
 #endif

@@ -624,3 +624,26 @@ def ref_csr_op(op, n_rows, n_cols, rp, ci, va):
     getattr(ref(), f"ref_csr_op_{_v(va.dtype)}_{_i(rp.dtype)}")(int(op), i64(n_rows), i64(n_cols), i64(len(ci)), P(rp),
                                                                 P(ci), P(va), P(out_rp), P(out_ci), P(out_va))
     return out_rp, out_ci, out_va
+
+
+# ---- files: the reference's own reader / writer (gko::read_generic_raw, write_raw, write_binary_raw)
+def ref_mtx_read(path, cap=1 << 22):
+    """Returns ((n_rows, n_cols), rows, cols, vals) or raises RuntimeError when the reference throws."""
+    dims = np.zeros(2, dtype=np.int64)
+    rows, cols = np.zeros(cap, dtype=np.int64), np.zeros(cap, dtype=np.int64)
+    vals = np.zeros(cap)
+    fn = ref().ref_mtx_read
+    fn.restype = i64
+    n = fn(str(path).encode(), P(dims), i64(cap), P(rows), P(cols), P(vals))
+    if n < 0:
+        raise RuntimeError(f"reference reader failed ({n})")
+    return (int(dims[0]), int(dims[1])), rows[:n].copy(), cols[:n].copy(), vals[:n].copy()
+
+
+def ref_mtx_write(path, size, rows, cols, vals, binary=False, index32=False, value32=False):
+    r, c = np.ascontiguousarray(rows, dtype=np.int64), np.ascontiguousarray(cols, dtype=np.int64)
+    v = np.ascontiguousarray(vals, dtype=np.float64)
+    rc = ref().ref_mtx_write(str(path).encode(), int(binary), i64(size[0]), i64(size[1]), i64(len(v)), P(r), P(c), P(v),
+                             int(index32), int(value32))
+    if rc:
+        raise RuntimeError(f"reference writer failed ({rc})")

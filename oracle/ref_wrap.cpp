@@ -12,6 +12,7 @@
 #include <omp.h>
 
 #include <chrono>
+#include <fstream>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -438,9 +439,73 @@ int csr_op_impl(int op, int64_t n_rows, int64_t n_cols, int64_t nnz, const I* rp
     return 0;
 }
 
+// gko::read_generic_raw / write_raw / write_binary_raw on a file
+int64_t mtx_read_impl(const char* path, int64_t* dims, int64_t cap, int64_t* rows, int64_t* cols, double* vals)
+{
+    std::ifstream in(path, std::ios::binary);
+    if (!in) return -2;
+    try {
+        auto data = gko::read_generic_raw<double, gko::int64>(in);
+        dims[0] = data.size[0];
+        dims[1] = data.size[1];
+        const int64_t n = static_cast<int64_t>(data.nonzeros.size());
+        if (n > cap) return -3;
+        for (int64_t i = 0; i < n; ++i) {
+            rows[i] = data.nonzeros[i].row;
+            cols[i] = data.nonzeros[i].column;
+            vals[i] = data.nonzeros[i].value;
+        }
+        return n;
+    } catch (const std::exception&) {
+        return -1;
+    }
+}
+
+int mtx_write_impl(const char* path, int format, int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t* rows,
+                   const int64_t* cols, const double* vals, int index32, int value32)
+{
+    std::ofstream out(path, std::ios::binary);
+    if (!out) return -2;
+    auto fill = [&](auto& data) {
+        for (int64_t i = 0; i < nnz; ++i) data.nonzeros.emplace_back(rows[i], cols[i], vals[i]);
+    };
+    if (format == 0) {
+        gko::matrix_data<double, gko::int64> d(gko::dim<2>(n_rows, n_cols));
+        fill(d);
+        gko::write_raw(out, d, gko::layout_type::coordinate);
+    } else if (index32 && value32) {
+        gko::matrix_data<float, gko::int32> d(gko::dim<2>(n_rows, n_cols));
+        fill(d);
+        gko::write_binary_raw(out, d);
+    } else if (index32) {
+        gko::matrix_data<double, gko::int32> d(gko::dim<2>(n_rows, n_cols));
+        fill(d);
+        gko::write_binary_raw(out, d);
+    } else if (value32) {
+        gko::matrix_data<float, gko::int64> d(gko::dim<2>(n_rows, n_cols));
+        fill(d);
+        gko::write_binary_raw(out, d);
+    } else {
+        gko::matrix_data<double, gko::int64> d(gko::dim<2>(n_rows, n_cols));
+        fill(d);
+        gko::write_binary_raw(out, d);
+    }
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
+
+int64_t ref_mtx_read(const char* path, int64_t* dims, int64_t cap, int64_t* rows, int64_t* cols, double* vals)
+{
+    return mtx_read_impl(path, dims, cap, rows, cols, vals);
+}
+int ref_mtx_write(const char* path, int format, int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t* rows,
+                  const int64_t* cols, const double* vals, int index32, int value32)
+{
+    return mtx_write_impl(path, format, n_rows, n_cols, nnz, rows, cols, vals, index32, value32);
+}
 
 int ref_num_threads(void) { return omp_get_max_threads(); }
 void ref_set_num_threads(int n) { omp_set_num_threads(n); }

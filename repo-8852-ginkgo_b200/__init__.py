@@ -47,7 +47,7 @@ from .core import (  # noqa: E402,F401
     check,
     current_stream,
 )
-from . import matrix, solver, preconditioner, stop, gen, distributed, assembly  # noqa: E402,F401
+from . import matrix, solver, preconditioner, stop, gen, distributed, assembly, io  # noqa: E402,F401
 
 __all__ = [
     "lib",

@@ -144,6 +144,14 @@ def declare(lib):
             d(f"gkob200_coo_remove_zeros_{V}_{I}", [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, sz])
             d(f"gkob200_csr_transpose_{V}_{I}", [vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, sz])
             d(f"gkob200_csr_sort_by_column_index_{V}_{I}", [vp, i64, i64, i64, vp, vp, vp, vp, sz])
+    # MatrixMarket / GINKGO binary files (host)
+    d("gkob200_mtx_last_error", [], C.c_char_p)
+    d("gkob200_mtx_read_open", [C.c_char_p, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)])
+    d("gkob200_mtx_read_close", [vp])
+    for V in VT:
+        for I in ("i32", "i64"):
+            d(f"gkob200_mtx_read_copy_{V}_{I}", [vp, vp, vp, vp])
+            d(f"gkob200_mtx_write_{V}_{I}", [C.c_char_p, C.c_int, C.c_int, i64, i64, i64, vp, vp, vp])
     # generators (host)
     d("gkob200_gen_stencil_nnz", [C.c_int, i64, i64, i64, i64, i64], i64)
     for V in VT:

@@ -98,3 +98,22 @@ def test_csr_read_of_shuffled_stencil_equals_generator(gko, exec_, ora):
     y = gko.matrix.Dense.create(exec_, (n, 1))
     A.apply(gko.matrix.Dense.from_numpy(exec_, x), y)
     assert np.array_equal(y.to_numpy(), ora.csr_spmv(rp, ci, va, x))
+
+
+@pytest.mark.parametrize("layout", ["coordinate", "binary"])
+def test_file_to_device_csr(gko, exec_, ora, tmp_path, layout):
+    """gko::read<Csr>(file, exec): written with write_raw / write_binary_raw in shuffled order, read
+    back through the native reader and the device assembly == the generator's CSR."""
+    rp, ci, va, n = gko.gen.stencil_csr("7pt", 30, 20, 10)
+    rows = np.repeat(np.arange(n, dtype=np.int32), np.diff(rp))
+    p = np.random.default_rng(2).permutation(len(ci))
+    path = tmp_path / ("m.mtx" if layout == "coordinate" else "m.bin")
+    gko.io.write_raw(path, (n, n), rows[p], ci[p], va[p], layout=gko.io.COORDINATE if layout == "coordinate" else gko.io.BINARY,
+                     precision=17)
+    A = gko.io.read(exec_, path)
+    assert A.size == (n, n)
+    assert np.array_equal(npy(A.row_ptrs), rp) and np.array_equal(npy(A.col_idxs), ci) and np.array_equal(npy(A.values), va)
+    x = np.random.default_rng(1).standard_normal((n, 1))
+    y = gko.matrix.Dense.create(exec_, (n, 1))
+    A.apply(gko.matrix.Dense.from_numpy(exec_, x), y)
+    assert np.array_equal(y.to_numpy(), ora.csr_spmv(rp, ci, va, x))
