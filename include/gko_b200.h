@@ -292,6 +292,28 @@ GKOB200_DECL_JACOBI_SCALAR(f32, float)
  * hessenberg_iter points at column block `iter`; final_iter_nums are size_type (uint64).
  * ------------------------------------------------------------------------- */
 #define GKOB200_DECL_KRYLOV(V, VT)                                                                                \
+    /* FCG / CGS step kernels [ref: core/solver/{fcg,cgs}_kernels.hpp; oracle                      \
+     * reference/solver/fcg_kernels.cpp:50-128, cgs_kernels.cpp:50-167] */                                         \
+    int gkob200_fcg_initialize_##V(void* stream, int64_t n, int64_t k, const VT* b, int64_t b_stride, VT* r,       \
+                                   VT* z, VT* p, VT* q, VT* t, int64_t stride, VT* prev_rho, VT* rho, VT* rho_t,   \
+                                   uint8_t* stop_status);                                                         \
+    int gkob200_fcg_step_1_##V(void* stream, int64_t n, int64_t k, VT* p, const VT* z, int64_t stride,             \
+                               const VT* rho_t, const VT* prev_rho, const uint8_t* stop_status);                   \
+    int gkob200_fcg_step_2_##V(void* stream, int64_t n, int64_t k, VT* x, int64_t x_stride, VT* r, VT* t,          \
+                               const VT* p, const VT* q, int64_t stride, const VT* beta, const VT* rho,            \
+                               const uint8_t* stop_status);                                                       \
+    int gkob200_cgs_initialize_##V(void* stream, int64_t n, int64_t k, const VT* b, int64_t b_stride, VT* r,       \
+                                   VT* r_tld, VT* p, VT* q, VT* u, VT* u_hat, VT* v_hat, VT* t, int64_t stride,    \
+                                   VT* alpha, VT* beta, VT* gamma, VT* rho_prev, VT* rho, uint8_t* stop_status);   \
+    int gkob200_cgs_step_1_##V(void* stream, int64_t n, int64_t k, const VT* r, VT* u, VT* p, const VT* q,         \
+                               int64_t stride, VT* beta, const VT* rho, const VT* rho_prev,                        \
+                               const uint8_t* stop_status);                                                       \
+    int gkob200_cgs_step_2_##V(void* stream, int64_t n, int64_t k, const VT* u, const VT* v_hat, VT* q, VT* t,     \
+                               int64_t stride, VT* alpha, const VT* rho, const VT* gamma,                          \
+                               const uint8_t* stop_status);                                                       \
+    int gkob200_cgs_step_3_##V(void* stream, int64_t n, int64_t k, const VT* t, const VT* u_hat, VT* r,            \
+                               int64_t stride, VT* x, int64_t x_stride, const VT* alpha,                           \
+                               const uint8_t* stop_status);                                                       \
     int gkob200_bicgstab_initialize_##V(void* stream, int64_t n, int64_t k, const VT* b, int64_t b_stride, VT* r,  \
                                         VT* rr, VT* y, VT* s, VT* t, VT* z, VT* v, VT* p, int64_t stride,          \
                                         VT* prev_rho, VT* rho, VT* alpha, VT* beta, VT* gamma, VT* omega,          \

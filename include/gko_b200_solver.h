@@ -109,7 +109,13 @@ typedef struct gkob200_stop {
 
 typedef struct gkob200_solver gkob200_solver;
 
-enum gkob200_solver_kind { GKOB200_SOLVER_CG = 0, GKOB200_SOLVER_BICGSTAB = 1, GKOB200_SOLVER_GMRES = 2 };
+enum gkob200_solver_kind {
+    GKOB200_SOLVER_CG = 0,
+    GKOB200_SOLVER_BICGSTAB = 1,
+    GKOB200_SOLVER_GMRES = 2,
+    GKOB200_SOLVER_FCG = 3, /* core/solver/fcg.cpp:104-196 */
+    GKOB200_SOLVER_CGS = 4  /* core/solver/cgs.cpp:104-212 */
+};
 
 /* generate: blocking; allocates the solver workspace on the current device.
  * krylov_dim only for GMRES [ref: include/ginkgo/core/solver/gmres.hpp:57]. */

@@ -93,7 +93,7 @@ def cg_solve(rp, ci, va, b, x0, precond=0, inv_diag=None, max_iters=1000, factor
 
 # ---- compiled reference -----------------------------------------------------
 FORMATS = {"csr": 0, "ell": 1, "sellp": 2, "coo": 3, "hybrid": 4}
-SOLVERS = {"cg": 0, "bicgstab": 1, "gmres": 2}
+SOLVERS = {"cg": 0, "bicgstab": 1, "gmres": 2, "fcg": 3, "cgs": 4}
 
 
 def ref_spmv(rp, ci, va, b, n_cols=None, alpha=None, beta=None, c=None, fmt="csr", hybrid_limit=-1, omp=False,
@@ -358,7 +358,7 @@ def _precond_struct(dtype, precond, inv_diag, J):
 
 def krylov_solve(solver, rp, ci, va, b, x0, precond=0, inv_diag=None, J=None, max_iters=1000, factor=1e-8,
                  baseline=0, krylov_dim=30):
-    """solver in {"bicgstab", "gmres"}; precond 0 none / 1 scalar Jacobi (inv_diag) / 2 block Jacobi (J from
+    """solver in {"bicgstab", "gmres", "fcg", "cgs"}; precond 0 none / 1 scalar Jacobi (inv_diag) / 2 block Jacobi (J from
     jacobi_block_generate).  Returns (x, iterations, residual_history, stop_status)."""
     n = len(rp) - 1
     b2 = np.ascontiguousarray(b.reshape(n, -1))
@@ -368,8 +368,8 @@ def krylov_solve(solver, rp, ci, va, b, x0, precond=0, inv_diag=None, J=None, ma
     hist = np.zeros(max_iters + 2, dtype=va.dtype)
     stop = np.zeros(k, dtype=np.uint8)
     p = _precond_struct(va.dtype, precond, inv_diag, J)
-    if solver == "bicgstab":
-        fn = getattr(lib(), f"oracle_bicgstab_solve_csr_i32_{V}")
+    if solver in ("bicgstab", "fcg", "cgs"):
+        fn = getattr(lib(), f"oracle_{solver}_solve_csr_i32_{V}")
         fn.restype = i64
         it = fn(i64(n), P(rp), P(ci), P(va), C.byref(p), i64(max_iters), _c(va.dtype, factor), int(baseline), i64(k),
                 P(b2), P(x), P(hist), i64(len(hist)), P(stop))

@@ -154,7 +154,7 @@ int spmv_impl(int exec_kind, int format, int64_t hybrid_limit, int64_t n_rows, i
     }
 }
 
-// solver_kind 0 CG, 1 BiCGSTAB, 2 GMRES; precond_block: 0 none, 1 scalar Jacobi, >1 block Jacobi
+// solver_kind 0 CG, 1 BiCGSTAB, 2 GMRES, 3 FCG, 4 CGS; precond_block: 0 none, 1 scalar Jacobi, >1 block Jacobi
 template <typename V, typename I>
 int64_t solve_impl(int exec_kind, int solver_kind, int format, int64_t hybrid_limit, int64_t n, int64_t nnz,
                    const I* rp, const I* ci, const V* va, int precond_block, int64_t max_iters, double factor,
@@ -198,6 +198,14 @@ int64_t solve_impl(int exec_kind, int solver_kind, int format, int64_t hybrid_li
         } else if (solver_kind == 2) {
             auto f = gko::solver::Gmres<V>::build().with_criteria(crit).with_krylov_dim(
                 static_cast<gko::size_type>(krylov_dim));
+            if (M) f.with_generated_preconditioner(M);
+            solver = f.on(exec)->generate(A);
+        } else if (solver_kind == 3) {
+            auto f = gko::solver::Fcg<V>::build().with_criteria(crit);
+            if (M) f.with_generated_preconditioner(M);
+            solver = f.on(exec)->generate(A);
+        } else if (solver_kind == 4) {
+            auto f = gko::solver::Cgs<V>::build().with_criteria(crit);
             if (M) f.with_generated_preconditioner(M);
             solver = f.on(exec)->generate(A);
         } else {

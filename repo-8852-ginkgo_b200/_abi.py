@@ -17,7 +17,7 @@ I32, I64 = 0, 1
 FMT_CSR, FMT_ELL, FMT_SELLP, FMT_COO, FMT_HYBRID, FMT_CSR_ROWS = range(6)
 PRECOND_NONE, PRECOND_JACOBI_SCALAR, PRECOND_JACOBI_BLOCK = range(3)
 STOP_RHS_NORM, STOP_INITIAL_RESNORM, STOP_ABSOLUTE = range(3)
-SOLVER_CG, SOLVER_BICGSTAB, SOLVER_GMRES = range(3)
+SOLVER_CG, SOLVER_BICGSTAB, SOLVER_GMRES, SOLVER_FCG, SOLVER_CGS = range(5)
 
 
 class Matrix(C.Structure):
@@ -119,6 +119,13 @@ def declare(lib):
         d(f"gkob200_row_len_histogram_{I}", [vp, vp, i64, u64, u64, C.c_int, vp])
     # Krylov step kernels
     for V, T in VT.items():
+        d(f"gkob200_fcg_initialize_{V}", [vp, i64, i64, vp, i64] + [vp] * 5 + [i64] + [vp] * 4)
+        d(f"gkob200_fcg_step_1_{V}", [vp, i64, i64, vp, vp, i64, vp, vp, vp])
+        d(f"gkob200_fcg_step_2_{V}", [vp, i64, i64, vp, i64, vp, vp, vp, vp, i64, vp, vp, vp])
+        d(f"gkob200_cgs_initialize_{V}", [vp, i64, i64, vp, i64] + [vp] * 8 + [i64] + [vp] * 6)
+        d(f"gkob200_cgs_step_1_{V}", [vp, i64, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp])
+        d(f"gkob200_cgs_step_2_{V}", [vp, i64, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp])
+        d(f"gkob200_cgs_step_3_{V}", [vp, i64, i64, vp, vp, vp, i64, vp, i64, vp, vp])
         d(f"gkob200_bicgstab_initialize_{V}", [vp, i64, i64, vp, i64] + [vp] * 8 + [i64] + [vp] * 7)
         d(f"gkob200_bicgstab_step_1_{V}", [vp, i64, i64, vp, vp, vp, i64, vp, vp, vp, vp, vp])
         d(f"gkob200_bicgstab_step_2_{V}", [vp, i64, i64, vp, vp, vp, i64, vp, vp, vp, vp])

@@ -113,6 +113,132 @@ int bicgstab_finalize(void* st, int64_t n, int64_t k, V* x, int64_t xs, const V*
     });
 }
 
+// --------------------------------- FCG / CGS ----------------------------------
+// 1:1 with the reference kernels [fcg: common/unified/solver/fcg_kernels.cpp, oracle
+// reference/solver/fcg_kernels.cpp:50-128; cgs: common/unified/solver/cgs_kernels.cpp, oracle
+// reference/solver/cgs_kernels.cpp:50-167].
+template <typename V>
+int fcg_initialize(void* st, int64_t n, int64_t k, const V* b, int64_t bs, V* r, V* z, V* p, V* q, V* t, int64_t s,
+                   V* prev_rho, V* rho, V* rho_t, uint8_t* stop)
+{
+    if (n < 0 || k < 0) return GKOB200_EINVAL;
+    if (k == 0) return 0;
+    int rc = launch_2d(as_stream(st), 1, k, [=] __device__(int64_t, int64_t j) {
+        rho[j] = V(0);
+        prev_rho[j] = rho_t[j] = V(1);
+        stop[j] = 0;
+    });
+    if (rc) return rc;
+    return launch_2d(as_stream(st), n, k, [=] __device__(int64_t i, int64_t j) {
+        t[i * s + j] = r[i * s + j] = b[i * bs + j];
+        z[i * s + j] = p[i * s + j] = q[i * s + j] = V(0);
+    });
+}
+
+template <typename V>
+int fcg_step_1(void* st, int64_t n, int64_t k, V* p, const V* z, int64_t s, const V* rho_t, const V* prev_rho,
+               const uint8_t* stop)
+{
+    if (n < 0 || k < 0) return GKOB200_EINVAL;
+    return launch_2d(as_stream(st), n, k, [=] __device__(int64_t i, int64_t j) {
+        if (status_has_stopped(stop[j])) return;
+        const V pr = prev_rho[j];
+        p[i * s + j] = pr == V(0) ? z[i * s + j] : add_rn(z[i * s + j], mul_rn(div_rn(rho_t[j], pr), p[i * s + j]));
+    });
+}
+
+template <typename V>
+int fcg_step_2(void* st, int64_t n, int64_t k, V* x, int64_t xs, V* r, V* t, const V* p, const V* q, int64_t s,
+               const V* beta, const V* rho, const uint8_t* stop)
+{
+    if (n < 0 || k < 0) return GKOB200_EINVAL;
+    return launch_2d(as_stream(st), n, k, [=] __device__(int64_t i, int64_t j) {
+        if (status_has_stopped(stop[j])) return;
+        const V be = beta[j];
+        if (be == V(0)) return;
+        const V tmp = div_rn(rho[j], be);
+        const V prev_r = r[i * s + j];
+        x[i * xs + j] = add_rn(x[i * xs + j], mul_rn(tmp, p[i * s + j]));
+        const V nr = sub_rn(prev_r, mul_rn(tmp, q[i * s + j]));
+        r[i * s + j] = nr;
+        t[i * s + j] = sub_rn(nr, prev_r);
+    });
+}
+
+template <typename V>
+int cgs_initialize(void* st, int64_t n, int64_t k, const V* b, int64_t bs, V* r, V* r_tld, V* p, V* q, V* u, V* u_hat,
+                   V* v_hat, V* t, int64_t s, V* alpha, V* beta, V* gamma, V* rho_prev, V* rho, uint8_t* stop)
+{
+    if (n < 0 || k < 0) return GKOB200_EINVAL;
+    if (k == 0) return 0;
+    int rc = launch_2d(as_stream(st), 1, k, [=] __device__(int64_t, int64_t j) {
+        rho[j] = V(0);
+        rho_prev[j] = alpha[j] = beta[j] = gamma[j] = V(1);
+        stop[j] = 0;
+    });
+    if (rc) return rc;
+    return launch_2d(as_stream(st), n, k, [=] __device__(int64_t i, int64_t j) {
+        r[i * s + j] = r_tld[i * s + j] = b[i * bs + j];
+        u[i * s + j] = u_hat[i * s + j] = p[i * s + j] = q[i * s + j] = v_hat[i * s + j] = t[i * s + j] = V(0);
+    });
+}
+
+// beta is only updated where rho_prev != 0 (it keeps its previous value otherwise): the scalar
+// update is its own launch so that every vector entry sees the same beta
+template <typename V>
+int cgs_step_1(void* st, int64_t n, int64_t k, const V* r, V* u, V* p, const V* q, int64_t s, V* beta, const V* rho,
+               const V* rho_prev, const uint8_t* stop)
+{
+    if (n < 0 || k < 0) return GKOB200_EINVAL;
+    if (k == 0) return 0;
+    int rc = launch_2d(as_stream(st), 1, k, [=] __device__(int64_t, int64_t j) {
+        if (status_has_stopped(stop[j])) return;
+        if (rho_prev[j] != V(0)) beta[j] = div_rn(rho[j], rho_prev[j]);
+    });
+    if (rc) return rc;
+    return launch_2d(as_stream(st), n, k, [=] __device__(int64_t i, int64_t j) {
+        if (status_has_stopped(stop[j])) return;
+        const V be = beta[j];
+        const V qi = q[i * s + j];
+        const V ui = add_rn(r[i * s + j], mul_rn(be, qi));
+        u[i * s + j] = ui;
+        p[i * s + j] = add_rn(ui, mul_rn(be, add_rn(qi, mul_rn(be, p[i * s + j]))));
+    });
+}
+
+template <typename V>
+int cgs_step_2(void* st, int64_t n, int64_t k, const V* u, const V* v_hat, V* q, V* t, int64_t s, V* alpha, const V* rho,
+               const V* gamma, const uint8_t* stop)
+{
+    if (n < 0 || k < 0) return GKOB200_EINVAL;
+    if (k == 0) return 0;
+    int rc = launch_2d(as_stream(st), 1, k, [=] __device__(int64_t, int64_t j) {
+        if (status_has_stopped(stop[j])) return;
+        if (gamma[j] != V(0)) alpha[j] = div_rn(rho[j], gamma[j]);
+    });
+    if (rc) return rc;
+    return launch_2d(as_stream(st), n, k, [=] __device__(int64_t i, int64_t j) {
+        if (status_has_stopped(stop[j])) return;
+        const V ui = u[i * s + j];
+        const V qi = sub_rn(ui, mul_rn(alpha[j], v_hat[i * s + j]));
+        q[i * s + j] = qi;
+        t[i * s + j] = add_rn(ui, qi);
+    });
+}
+
+template <typename V>
+int cgs_step_3(void* st, int64_t n, int64_t k, const V* t, const V* u_hat, V* r, int64_t s, V* x, int64_t xs,
+               const V* alpha, const uint8_t* stop)
+{
+    if (n < 0 || k < 0) return GKOB200_EINVAL;
+    return launch_2d(as_stream(st), n, k, [=] __device__(int64_t i, int64_t j) {
+        if (status_has_stopped(stop[j])) return;
+        const V a = alpha[j];
+        x[i * xs + j] = add_rn(x[i * xs + j], mul_rn(a, u_hat[i * s + j]));
+        r[i * s + j] = sub_rn(r[i * s + j], mul_rn(a, t[i * s + j]));
+    });
+}
+
 // --------------------------------- GMRES --------------------------------------
 template <typename V>
 int gmres_initialize(void* st, int64_t n, int64_t k, int64_t krylov_dim, const V* b, int64_t bs, V* residual,
@@ -272,6 +398,29 @@ using namespace gkob200;
 extern "C" {
 
 #define GKOB200_DEF_KRYLOV(V, VT)                                                                                 \
+    int gkob200_fcg_initialize_##V(void* st, int64_t n, int64_t k, const VT* b, int64_t bs, VT* r, VT* z, VT* p,   \
+                                   VT* q, VT* t, int64_t s, VT* prev_rho, VT* rho, VT* rho_t, uint8_t* stop)       \
+    { return fcg_initialize<VT>(st, n, k, b, bs, r, z, p, q, t, s, prev_rho, rho, rho_t, stop); }                  \
+    int gkob200_fcg_step_1_##V(void* st, int64_t n, int64_t k, VT* p, const VT* z, int64_t s, const VT* rho_t,     \
+                               const VT* prev_rho, const uint8_t* stop)                                           \
+    { return fcg_step_1<VT>(st, n, k, p, z, s, rho_t, prev_rho, stop); }                                           \
+    int gkob200_fcg_step_2_##V(void* st, int64_t n, int64_t k, VT* x, int64_t xs, VT* r, VT* t, const VT* p,       \
+                               const VT* q, int64_t s, const VT* beta, const VT* rho, const uint8_t* stop)         \
+    { return fcg_step_2<VT>(st, n, k, x, xs, r, t, p, q, s, beta, rho, stop); }                                    \
+    int gkob200_cgs_initialize_##V(void* st, int64_t n, int64_t k, const VT* b, int64_t bs, VT* r, VT* r_tld,      \
+                                   VT* p, VT* q, VT* u, VT* u_hat, VT* v_hat, VT* t, int64_t s, VT* alpha,         \
+                                   VT* beta, VT* gamma, VT* rho_prev, VT* rho, uint8_t* stop)                      \
+    { return cgs_initialize<VT>(st, n, k, b, bs, r, r_tld, p, q, u, u_hat, v_hat, t, s, alpha, beta, gamma,        \
+                                rho_prev, rho, stop); }                                                           \
+    int gkob200_cgs_step_1_##V(void* st, int64_t n, int64_t k, const VT* r, VT* u, VT* p, const VT* q, int64_t s,  \
+                               VT* beta, const VT* rho, const VT* rho_prev, const uint8_t* stop)                   \
+    { return cgs_step_1<VT>(st, n, k, r, u, p, q, s, beta, rho, rho_prev, stop); }                                 \
+    int gkob200_cgs_step_2_##V(void* st, int64_t n, int64_t k, const VT* u, const VT* v_hat, VT* q, VT* t,         \
+                               int64_t s, VT* alpha, const VT* rho, const VT* gamma, const uint8_t* stop)          \
+    { return cgs_step_2<VT>(st, n, k, u, v_hat, q, t, s, alpha, rho, gamma, stop); }                               \
+    int gkob200_cgs_step_3_##V(void* st, int64_t n, int64_t k, const VT* t, const VT* u_hat, VT* r, int64_t s,     \
+                               VT* x, int64_t xs, const VT* alpha, const uint8_t* stop)                           \
+    { return cgs_step_3<VT>(st, n, k, t, u_hat, r, s, x, xs, alpha, stop); }                                       \
     int gkob200_bicgstab_initialize_##V(void* st, int64_t n, int64_t k, const VT* b, int64_t bs, VT* r, VT* rr,    \
                                         VT* y, VT* s_, VT* t, VT* z, VT* v, VT* p, int64_t s, VT* prev_rho,        \
                                         VT* rho, VT* alpha, VT* beta, VT* gamma, VT* omega, uint8_t* stop)         \

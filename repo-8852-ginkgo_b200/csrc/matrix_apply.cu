@@ -179,6 +179,10 @@ int gkob200_solver_create(int kind, const gkob200_matrix* A, const gkob200_preco
     }
     else if (kind == GKOB200_SOLVER_BICGSTAB) {
         s = A->value_type == GKOB200_F64 ? make_bicgstab_f64(A, M, stop, nrhs, &rc) : make_bicgstab_f32(A, M, stop, nrhs, &rc);
+    } else if (kind == GKOB200_SOLVER_FCG) {
+        s = make_fcg(A, M, stop, nrhs, &rc);
+    } else if (kind == GKOB200_SOLVER_CGS) {
+        s = make_cgs(A, M, stop, nrhs, &rc);
     } else if (kind == GKOB200_SOLVER_GMRES) {
         s = A->value_type == GKOB200_F64 ? make_gmres_f64(A, M, stop, nrhs, krylov_dim, &rc)
                                          : make_gmres_f32(A, M, stop, nrhs, krylov_dim, &rc);

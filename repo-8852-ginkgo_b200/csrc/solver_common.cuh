@@ -131,6 +131,13 @@ GKOB200_TYPED2(dense_compute_dot)
 GKOB200_TYPED2(dense_compute_norm2)
 GKOB200_TYPED2(jacobi_simple_scalar_apply)
 GKOB200_TYPED2(jacobi_block_simple_apply)
+GKOB200_TYPED2(fcg_initialize)
+GKOB200_TYPED2(fcg_step_1)
+GKOB200_TYPED2(fcg_step_2)
+GKOB200_TYPED2(cgs_initialize)
+GKOB200_TYPED2(cgs_step_1)
+GKOB200_TYPED2(cgs_step_2)
+GKOB200_TYPED2(cgs_step_3)
 GKOB200_TYPED2(bicgstab_initialize)
 GKOB200_TYPED2(bicgstab_step_1)
 GKOB200_TYPED2(bicgstab_step_2)
@@ -297,6 +304,8 @@ gkob200_solver* make_bicgstab_f64(const gkob200_matrix*, const gkob200_precond*,
 gkob200_solver* make_bicgstab_f32(const gkob200_matrix*, const gkob200_precond*, const gkob200_stop*, int64_t nrhs, int* rc);
 gkob200_solver* make_gmres_f64(const gkob200_matrix*, const gkob200_precond*, const gkob200_stop*, int64_t nrhs, int64_t krylov_dim, int* rc);
 gkob200_solver* make_gmres_f32(const gkob200_matrix*, const gkob200_precond*, const gkob200_stop*, int64_t nrhs, int64_t krylov_dim, int* rc);
+gkob200_solver* make_fcg(const gkob200_matrix*, const gkob200_precond*, const gkob200_stop*, int64_t nrhs, int* rc);
+gkob200_solver* make_cgs(const gkob200_matrix*, const gkob200_precond*, const gkob200_stop*, int64_t nrhs, int* rc);
 
 gkob200_solver* make_cg_f64(const gkob200_matrix*, const gkob200_precond*, const gkob200_stop*, int64_t nrhs, int* rc);
 gkob200_solver* make_cg_f32(const gkob200_matrix*, const gkob200_precond*, const gkob200_stop*, int64_t nrhs, int* rc);

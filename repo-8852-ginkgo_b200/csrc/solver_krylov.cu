@@ -503,6 +503,134 @@ struct GmresSolver : SolverBase<V> {
     }
 };
 
+// ------------------------------------------------------------------------------
+// FCG and CGS: the reference loops (core/solver/fcg.cpp:104-196,
+// core/solver/cgs.cpp:104-212) kernel by kernel, with the criterion on the device like the
+// BiCGSTAB / GMRES general paths.  Any number of right-hand sides.
+template <typename V>
+struct FcgSolver : SolverBase<V> {
+    using B = SolverBase<V>;
+    using B::A; using B::M; using B::k; using B::n; using B::stop; using B::ws; using B::launch_count;
+    DevBuf vecs, scal;
+    V* vec(int i) { return vecs.as<V>() + static_cast<int64_t>(i) * n * k; }
+    V* sc(int i) { return scal.as<V>() + static_cast<int64_t>(i) * k; }
+
+    int init()
+    {
+        int rc = this->init_base();
+        if (rc) return rc;
+        if ((rc = vecs.alloc(static_cast<size_t>(n) * k * 5 * sizeof(V)))) return rc;
+        return scal.alloc(static_cast<size_t>(k) * 4 * sizeof(V));
+    }
+
+    int apply(cudaStream_t s, const void* b_, int64_t bs, void* x_, int64_t xs) override
+    {
+        const V* b = static_cast<const V*>(b_);
+        V* x = static_cast<V*>(x_);
+        V* tag = B::tag();
+        launch_count = 0;
+        this->num_iterations = 0;
+        if (n == 0) return 0;
+        if (!b || !x) return GKOB200_EINVAL;
+        V *r = vec(0), *z = vec(1), *p = vec(2), *q = vec(3), *t = vec(4);
+        V *beta = sc(0), *prev_rho = sc(1), *rho = sc(2), *rho_t = sc(3);
+        uint8_t* stat = this->stat();
+        int rc;
+        if ((rc = this->reset_state(s))) return rc;
+        if ((rc = typed::fcg_initialize(tag, s, n, k, b, bs, r, z, p, q, t, k, prev_rho, rho, rho_t, stat))) return rc;
+        if ((rc = matrix_apply<V>(s, A, x, xs, k, this->neg_one(), this->one(), r, k, nullptr))) return rc;
+        if ((rc = this->baseline_norm(s, b, bs, r, k))) return rc;
+        launch_count += 3;
+        int64_t it = 0;
+        bool stopped = false;
+        while (true) {
+            if ((rc = this->precond_apply(s, r, k, z, k))) return rc;
+            if ((rc = typed::dense_compute_dot(tag, s, n, k, r, k, z, k, rho, ws.p))) return rc;
+            if ((rc = typed::dense_compute_dot(tag, s, n, k, t, k, z, k, rho_t, ws.p))) return rc;
+            if ((rc = typed::dense_compute_norm2(tag, s, n, k, r, k, this->tau(), ws.p))) return rc;
+            if ((rc = this->check(s, this->tau(), true, true))) return rc;
+            launch_count += 3;
+            if (it % this->chunk == 0 || it >= stop.max_iters) {
+                if ((rc = this->poll(s, &stopped))) return rc;
+                if (stopped) break;
+            }
+            if ((rc = typed::fcg_step_1(tag, s, n, k, p, z, k, rho_t, prev_rho, stat))) return rc;
+            if ((rc = matrix_apply<V>(s, A, p, k, k, nullptr, nullptr, q, k, nullptr))) return rc;
+            if ((rc = typed::dense_compute_dot(tag, s, n, k, p, k, q, k, beta, ws.p))) return rc;
+            if ((rc = typed::fcg_step_2(tag, s, n, k, x, xs, r, t, p, q, k, beta, rho, stat))) return rc;
+            // swap(prev_rho, rho): rho is recomputed at the top, a copy is equivalent
+            if ((rc = typed::dense_copy(tag, s, int64_t(1), k, rho, k, prev_rho, k))) return rc;
+            launch_count += 5;
+            ++it;
+        }
+        return this->finish(s);
+    }
+};
+
+template <typename V>
+struct CgsSolver : SolverBase<V> {
+    using B = SolverBase<V>;
+    using B::A; using B::M; using B::k; using B::n; using B::stop; using B::ws; using B::launch_count;
+    DevBuf vecs, scal;
+    V* vec(int i) { return vecs.as<V>() + static_cast<int64_t>(i) * n * k; }
+    V* sc(int i) { return scal.as<V>() + static_cast<int64_t>(i) * k; }
+
+    int init()
+    {
+        int rc = this->init_base();
+        if (rc) return rc;
+        if ((rc = vecs.alloc(static_cast<size_t>(n) * k * 8 * sizeof(V)))) return rc;
+        return scal.alloc(static_cast<size_t>(k) * 5 * sizeof(V));
+    }
+
+    int apply(cudaStream_t s, const void* b_, int64_t bs, void* x_, int64_t xs) override
+    {
+        const V* b = static_cast<const V*>(b_);
+        V* x = static_cast<V*>(x_);
+        V* tag = B::tag();
+        launch_count = 0;
+        this->num_iterations = 0;
+        if (n == 0) return 0;
+        if (!b || !x) return GKOB200_EINVAL;
+        V *r = vec(0), *r_tld = vec(1), *p = vec(2), *q = vec(3), *u = vec(4), *u_hat = vec(5), *v_hat = vec(6), *t = vec(7);
+        V *alpha = sc(0), *beta = sc(1), *gamma = sc(2), *prev_rho = sc(3), *rho = sc(4);
+        uint8_t* stat = this->stat();
+        int rc;
+        if ((rc = this->reset_state(s))) return rc;
+        if ((rc = typed::cgs_initialize(tag, s, n, k, b, bs, r, r_tld, p, q, u, u_hat, v_hat, t, k, alpha, beta, gamma,
+                                        prev_rho, rho, stat)))
+            return rc;
+        if ((rc = matrix_apply<V>(s, A, x, xs, k, this->neg_one(), this->one(), r, k, nullptr))) return rc;
+        if ((rc = this->baseline_norm(s, b, bs, r, k))) return rc;
+        if ((rc = typed::dense_copy(tag, s, n, k, r, k, r_tld, k))) return rc;
+        launch_count += 4;
+        int64_t it = 0;
+        bool stopped = false;
+        while (true) {
+            if ((rc = typed::dense_compute_dot(tag, s, n, k, r, k, r_tld, k, rho, ws.p))) return rc;
+            if ((rc = typed::dense_compute_norm2(tag, s, n, k, r, k, this->tau(), ws.p))) return rc;
+            if ((rc = this->check(s, this->tau(), true, true))) return rc;
+            launch_count += 2;
+            if (it % this->chunk == 0 || it >= stop.max_iters) {
+                if ((rc = this->poll(s, &stopped))) return rc;
+                if (stopped) break;
+            }
+            if ((rc = typed::cgs_step_1(tag, s, n, k, r, u, p, q, k, beta, rho, prev_rho, stat))) return rc;
+            if ((rc = this->precond_apply(s, p, k, t, k))) return rc;
+            if ((rc = matrix_apply<V>(s, A, t, k, k, nullptr, nullptr, v_hat, k, nullptr))) return rc;
+            if ((rc = typed::dense_compute_dot(tag, s, n, k, r_tld, k, v_hat, k, gamma, ws.p))) return rc;
+            if ((rc = typed::cgs_step_2(tag, s, n, k, u, v_hat, q, t, k, alpha, rho, gamma, stat))) return rc;
+            if ((rc = this->precond_apply(s, t, k, u_hat, k))) return rc;
+            if ((rc = matrix_apply<V>(s, A, u_hat, k, k, nullptr, nullptr, t, k, nullptr))) return rc;
+            if ((rc = typed::cgs_step_3(tag, s, n, k, t, u_hat, r, k, x, xs, alpha, stat))) return rc;
+            if ((rc = typed::dense_copy(tag, s, int64_t(1), k, rho, k, prev_rho, k))) return rc;
+            launch_count += 9;
+            ++it;
+        }
+        return this->finish(s);
+    }
+};
+
 template <typename S>
 gkob200_solver* make(const gkob200_matrix* A, const gkob200_precond* M, const gkob200_stop* stop, int64_t nrhs,
                      int64_t krylov_dim, int* rc)
@@ -539,6 +667,16 @@ gkob200_solver* make_bicgstab_f64(const gkob200_matrix* A, const gkob200_precond
 gkob200_solver* make_bicgstab_f32(const gkob200_matrix* A, const gkob200_precond* M, const gkob200_stop* st, int64_t nrhs, int* rc)
 {
     return make<BicgstabSolver<float>>(A, M, st, nrhs, 0, rc);
+}
+gkob200_solver* make_fcg(const gkob200_matrix* A, const gkob200_precond* M, const gkob200_stop* st, int64_t nrhs, int* rc)
+{
+    return A->value_type == GKOB200_F64 ? make<FcgSolver<double>>(A, M, st, nrhs, 0, rc)
+                                        : make<FcgSolver<float>>(A, M, st, nrhs, 0, rc);
+}
+gkob200_solver* make_cgs(const gkob200_matrix* A, const gkob200_precond* M, const gkob200_stop* st, int64_t nrhs, int* rc)
+{
+    return A->value_type == GKOB200_F64 ? make<CgsSolver<double>>(A, M, st, nrhs, 0, rc)
+                                        : make<CgsSolver<float>>(A, M, st, nrhs, 0, rc);
 }
 gkob200_solver* make_gmres_f64(const gkob200_matrix* A, const gkob200_precond* M, const gkob200_stop* st, int64_t nrhs, int64_t m, int* rc)
 {

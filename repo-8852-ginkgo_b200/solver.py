@@ -134,3 +134,19 @@ class Gmres:
     @staticmethod
     def build():
         return _Factory(_abi.SOLVER_GMRES)
+
+
+class Fcg:
+    """solver::Fcg (reference core/solver/fcg.cpp)."""
+
+    @staticmethod
+    def build():
+        return _Factory(_abi.SOLVER_FCG)
+
+
+class Cgs:
+    """solver::Cgs (reference core/solver/cgs.cpp)."""
+
+    @staticmethod
+    def build():
+        return _Factory(_abi.SOLVER_CGS)

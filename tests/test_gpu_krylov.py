@@ -101,7 +101,7 @@ def test_reference_dense_kat(gko, exec_, kind):
     assert kat.rel_frobenius(x.to_numpy(), [[-4.0], [-1.0], [4.0]]) <= kat.rtol(np.float64) * 1e1
 
 
-@pytest.mark.parametrize("kind", ["Bicgstab", "Gmres"])
+@pytest.mark.parametrize("kind", ["Bicgstab", "Gmres", "Fcg", "Cgs"])
 @pytest.mark.parametrize("precond_block", [0, 1, 8, 32])
 @pytest.mark.parametrize("nrhs", [1, 2])
 def test_solvers_match_oracle(gko, exec_, ora, kind, precond_block, nrhs):
@@ -126,8 +126,12 @@ def test_solvers_match_oracle(gko, exec_, ora, kind, precond_block, nrhs):
     m = min(len(s.residual_history), len(hist_ref), 8)
     assert np.allclose(s.residual_history[:m], hist_ref[:m], rtol=1e-9)
     assert np.abs(dx.to_numpy() - x_ref).max() <= 1e-8 * np.abs(x_ref).max()
-    r = b - sp.csr_matrix((va, ci, rp), shape=(n, n)) @ dx.to_numpy()
-    assert np.all(np.linalg.norm(r, axis=0) <= 2e-10 * np.linalg.norm(b, axis=0))
+    Asp = sp.csr_matrix((va, ci, rp), shape=(n, n))
+    r = b - Asp @ dx.to_numpy()
+    # the true residual: as good as the criterion promises, or — where the recurrence residual
+    # drifts from it (FCG on this non-symmetric matrix) — as good as the reference's own solution
+    r_ref = np.linalg.norm(b - Asp @ x_ref, axis=0)
+    assert np.all(np.linalg.norm(r, axis=0) <= np.maximum(2e-10 * np.linalg.norm(b, axis=0), 2 * r_ref))
 
 
 @pytest.mark.parametrize("kind", ["Bicgstab", "Gmres"])

@@ -79,7 +79,7 @@ def test_block_jacobi_matches_reference(ora, refimpl, max_bs):
     assert np.array_equal(J["blocks"][d], R["blocks"][d])
 
 
-@pytest.mark.parametrize("solver", ["bicgstab", "gmres"])
+@pytest.mark.parametrize("solver", ["bicgstab", "gmres", "fcg", "cgs"])
 @pytest.mark.parametrize("precond_block", [0, 1, 8])
 @pytest.mark.parametrize("nrhs", [1, 2])
 def test_krylov_matches_reference(ora, refimpl, solver, precond_block, nrhs):
@@ -106,7 +106,7 @@ def test_krylov_matches_reference(ora, refimpl, solver, precond_block, nrhs):
 DENSE3 = [[1.0, -3.0, 0.0], [-4.0, 1.0, -3.0], [2.0, -1.0, 2.0]]
 
 
-@pytest.mark.parametrize("solver", ["bicgstab", "gmres"])
+@pytest.mark.parametrize("solver", ["bicgstab", "gmres", "cgs"])
 def test_solves_dense_system_kat(ora, solver):
     rp, ci, va, _ = kat.dense_to_csr(DENSE3)
     b = np.array([[-1.0], [3.0], [1.0]])
