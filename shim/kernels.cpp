@@ -32,6 +32,8 @@
 #include "core/preconditioner/jacobi_kernels.hpp"
 #include "core/solver/bicgstab_kernels.hpp"
 #include "core/solver/cg_kernels.hpp"
+#include "core/solver/cgs_kernels.hpp"
+#include "core/solver/fcg_kernels.hpp"
 #include "core/solver/common_gmres_kernels.hpp"
 #include "core/solver/gmres_kernels.hpp"
 #include "core/stop/criterion_kernels.hpp"
@@ -124,6 +126,15 @@ TYPED(dense_compute_sqrt)
 TYPED(cg_initialize)
 TYPED(cg_step_1)
 TYPED(cg_step_2)
+TYPED(fcg_initialize)
+TYPED(fcg_step_1)
+TYPED(fcg_step_2)
+TYPED(cgs_initialize)
+TYPED(cgs_step_1)
+TYPED(cgs_step_2)
+TYPED(cgs_step_3)
+TYPED_I(csr_transpose)
+TYPED_I(csr_sort_by_column_index)
 TYPED(bicgstab_initialize)
 TYPED(bicgstab_step_1)
 TYPED(bicgstab_step_2)
@@ -185,6 +196,35 @@ void extract_diagonal(Exec exec, const matrix::Csr<V, I>* orig, matrix::Diagonal
                                  orig->get_const_row_ptrs(), orig->get_const_col_idxs(), orig->get_const_values(),
                                  diag->get_values()));
 }
+
+// [cuda/matrix/csr_kernels.cu transpose (cusparse csr2csc) / sort_by_column_index (cusparse csrsort)]
+template <typename V, typename I>
+void transpose(Exec, const matrix::Csr<V, I>* orig, matrix::Csr<V, I>* trans)
+{
+    const int64_t n = (int64_t)orig->get_size()[0], m = (int64_t)orig->get_size()[1];
+    const int64_t nnz = (int64_t)orig->get_num_stored_elements();
+    const size_t wsb = gkob200_setup_sort_workspace_bytes(nnz, (int)sizeof(V), (int)sizeof(I));
+    B200(t::csr_transpose(V{}, I{}, kStream, n, m, nnz, orig->get_const_row_ptrs(), orig->get_const_col_idxs(),
+                          orig->get_const_values(), trans->get_row_ptrs(), trans->get_col_idxs(), trans->get_values(),
+                          scratch().get(wsb), wsb));
+}
+template <typename V, typename I>
+void sort_by_column_index(Exec, matrix::Csr<V, I>* to_sort)
+{
+    const int64_t n = (int64_t)to_sort->get_size()[0], m = (int64_t)to_sort->get_size()[1];
+    const int64_t nnz = (int64_t)to_sort->get_num_stored_elements();
+    const size_t wsb = gkob200_setup_sort_workspace_bytes(nnz, (int)sizeof(V), (int)sizeof(I));
+    B200(t::csr_sort_by_column_index(V{}, I{}, kStream, n, m, nnz, to_sort->get_const_row_ptrs(), to_sort->get_col_idxs(),
+                                     to_sort->get_values(), scratch().get(wsb), wsb));
+}
+template void transpose<double, int32>(Exec, const matrix::Csr<double, int32>*, matrix::Csr<double, int32>*);
+template void transpose<float, int32>(Exec, const matrix::Csr<float, int32>*, matrix::Csr<float, int32>*);
+template void transpose<double, int64>(Exec, const matrix::Csr<double, int64>*, matrix::Csr<double, int64>*);
+template void transpose<float, int64>(Exec, const matrix::Csr<float, int64>*, matrix::Csr<float, int64>*);
+template void sort_by_column_index<double, int32>(Exec, matrix::Csr<double, int32>*);
+template void sort_by_column_index<float, int32>(Exec, matrix::Csr<float, int32>*);
+template void sort_by_column_index<double, int64>(Exec, matrix::Csr<double, int64>*);
+template void sort_by_column_index<float, int64>(Exec, matrix::Csr<float, int64>*);
 
 #define INST_CSR(V, I)                                                                                     \
     template void spmv<V, I>(Exec, const matrix::Csr<V, I>*, const D<V>*, D<V>*);                           \
@@ -459,6 +499,93 @@ INST_CG(double)
 INST_CG(float)
 
 }  // namespace cg
+
+namespace fcg {
+
+template <typename V>
+void initialize(Exec, const D<V>* b, D<V>* r, D<V>* z, D<V>* p, D<V>* q, D<V>* t, D<V>* prev_rho, D<V>* rho,
+                D<V>* rho_t, array<stopping_status>* stop)
+{
+    B200(t::fcg_initialize(V{}, kStream, (int64_t)b->get_size()[0], (int64_t)b->get_size()[1], b->get_const_values(),
+                           (int64_t)b->get_stride(), r->get_values(), z->get_values(), p->get_values(), q->get_values(),
+                           t->get_values(), (int64_t)r->get_stride(), prev_rho->get_values(), rho->get_values(),
+                           rho_t->get_values(), status_ptr(stop)));
+}
+template <typename V>
+void step_1(Exec, D<V>* p, const D<V>* z, const D<V>* rho_t, const D<V>* prev_rho, const array<stopping_status>* stop)
+{
+    B200(t::fcg_step_1(V{}, kStream, (int64_t)p->get_size()[0], (int64_t)p->get_size()[1], p->get_values(),
+                       z->get_const_values(), (int64_t)p->get_stride(), rho_t->get_const_values(),
+                       prev_rho->get_const_values(), status_ptr(stop)));
+}
+template <typename V>
+void step_2(Exec, D<V>* x, D<V>* r, D<V>* t, const D<V>* p, const D<V>* q, const D<V>* beta, const D<V>* rho,
+            const array<stopping_status>* stop)
+{
+    B200(t::fcg_step_2(V{}, kStream, (int64_t)x->get_size()[0], (int64_t)x->get_size()[1], x->get_values(),
+                       (int64_t)x->get_stride(), r->get_values(), t->get_values(), p->get_const_values(),
+                       q->get_const_values(), (int64_t)r->get_stride(), beta->get_const_values(), rho->get_const_values(),
+                       status_ptr(stop)));
+}
+#define INST_FCG(V)                                                                                                 \
+    template void initialize<V>(Exec, const D<V>*, D<V>*, D<V>*, D<V>*, D<V>*, D<V>*, D<V>*, D<V>*, D<V>*,         \
+                                array<stopping_status>*);                                                          \
+    template void step_1<V>(Exec, D<V>*, const D<V>*, const D<V>*, const D<V>*, const array<stopping_status>*);     \
+    template void step_2<V>(Exec, D<V>*, D<V>*, D<V>*, const D<V>*, const D<V>*, const D<V>*, const D<V>*,         \
+                            const array<stopping_status>*);
+INST_FCG(double)
+INST_FCG(float)
+
+}  // namespace fcg
+
+namespace cgs {
+
+template <typename V>
+void initialize(Exec, const D<V>* b, D<V>* r, D<V>* r_tld, D<V>* p, D<V>* q, D<V>* u, D<V>* u_hat, D<V>* v_hat, D<V>* t,
+                D<V>* alpha, D<V>* beta, D<V>* gamma, D<V>* rho_prev, D<V>* rho, array<stopping_status>* stop)
+{
+    B200(t::cgs_initialize(V{}, kStream, (int64_t)b->get_size()[0], (int64_t)b->get_size()[1], b->get_const_values(),
+                           (int64_t)b->get_stride(), r->get_values(), r_tld->get_values(), p->get_values(),
+                           q->get_values(), u->get_values(), u_hat->get_values(), v_hat->get_values(), t->get_values(),
+                           (int64_t)r->get_stride(), alpha->get_values(), beta->get_values(), gamma->get_values(),
+                           rho_prev->get_values(), rho->get_values(), status_ptr(stop)));
+}
+template <typename V>
+void step_1(Exec, const D<V>* r, D<V>* u, D<V>* p, const D<V>* q, D<V>* beta, const D<V>* rho, const D<V>* rho_prev,
+            const array<stopping_status>* stop)
+{
+    B200(t::cgs_step_1(V{}, kStream, (int64_t)p->get_size()[0], (int64_t)p->get_size()[1], r->get_const_values(),
+                       u->get_values(), p->get_values(), q->get_const_values(), (int64_t)p->get_stride(),
+                       beta->get_values(), rho->get_const_values(), rho_prev->get_const_values(), status_ptr(stop)));
+}
+template <typename V>
+void step_2(Exec, const D<V>* u, const D<V>* v_hat, D<V>* q, D<V>* t, D<V>* alpha, const D<V>* rho, const D<V>* gamma,
+            const array<stopping_status>* stop)
+{
+    B200(t::cgs_step_2(V{}, kStream, (int64_t)u->get_size()[0], (int64_t)u->get_size()[1], u->get_const_values(),
+                       v_hat->get_const_values(), q->get_values(), t->get_values(), (int64_t)u->get_stride(),
+                       alpha->get_values(), rho->get_const_values(), gamma->get_const_values(), status_ptr(stop)));
+}
+template <typename V>
+void step_3(Exec, const D<V>* t, const D<V>* u_hat, D<V>* r, D<V>* x, const D<V>* alpha,
+            const array<stopping_status>* stop)
+{
+    B200(t::cgs_step_3(V{}, kStream, (int64_t)x->get_size()[0], (int64_t)x->get_size()[1], t->get_const_values(),
+                       u_hat->get_const_values(), r->get_values(), (int64_t)r->get_stride(), x->get_values(),
+                       (int64_t)x->get_stride(), alpha->get_const_values(), status_ptr(stop)));
+}
+#define INST_CGS(V)                                                                                                 \
+    template void initialize<V>(Exec, const D<V>*, D<V>*, D<V>*, D<V>*, D<V>*, D<V>*, D<V>*, D<V>*, D<V>*, D<V>*,  \
+                                D<V>*, D<V>*, D<V>*, D<V>*, array<stopping_status>*);                              \
+    template void step_1<V>(Exec, const D<V>*, D<V>*, D<V>*, const D<V>*, D<V>*, const D<V>*, const D<V>*,         \
+                            const array<stopping_status>*);                                                        \
+    template void step_2<V>(Exec, const D<V>*, const D<V>*, D<V>*, D<V>*, D<V>*, const D<V>*, const D<V>*,         \
+                            const array<stopping_status>*);                                                        \
+    template void step_3<V>(Exec, const D<V>*, const D<V>*, D<V>*, D<V>*, const D<V>*, const array<stopping_status>*);
+INST_CGS(double)
+INST_CGS(float)
+
+}  // namespace cgs
 
 namespace bicgstab {
 

@@ -1,7 +1,8 @@
 """The drop-in, end to end: shim/test_dropin.cpp is an ordinary Ginkgo program (public API
 only) linked against the UNMODIFIED Ginkgo core built from /root/reference (oracle/_ref/lib)
 and against shim/_build/libginkgo_cuda.so — the B200 shim over libgko_b200.so.  It runs
-Csr/Ell/Sellp/Coo/Hybrid::apply and Cg/Bicgstab/Gmres (+ scalar / block Jacobi) on
+Csr/Ell/Sellp/Coo/Hybrid::apply, Csr::transpose / sort_by_column_index and
+Cg/Fcg/Cgs/Bicgstab/Gmres (+ scalar / block Jacobi) on
 gko::CudaExecutor and compares with gko::ReferenceExecutor in the same process."""
 import os
 import subprocess
