@@ -451,7 +451,8 @@ GKOB200_DECL_SETUP(f32, float, i64, int64_t)
  * not fit the requested index type are rejected.  Errors return GKOB200_EINVAL and leave a
  * message in gkob200_mtx_last_error() (thread-local), the reference's stream-error texts.
  * gkob200_mtx_write_*: format 0 = "%%MatrixMarket matrix coordinate real general" (precision <= 0:
- * 6 significant digits, what the reference's ostream default gives), 1 = GINKGO binary.
+ * 6 significant digits, what the reference's ostream default gives), 1 = GINKGO binary,
+ * 2 = "%%MatrixMarket matrix array real general" (dense, column-major; what gko::write gives for Dense).
  * ------------------------------------------------------------------------- */
 const char* gkob200_mtx_last_error(void);
 int gkob200_mtx_read_open(const char* path, void** handle, int64_t* n_rows, int64_t* n_cols, int64_t* nnz);

@@ -640,10 +640,10 @@ def ref_mtx_read(path, cap=1 << 22):
     return (int(dims[0]), int(dims[1])), rows[:n].copy(), cols[:n].copy(), vals[:n].copy()
 
 
-def ref_mtx_write(path, size, rows, cols, vals, binary=False, index32=False, value32=False):
+def ref_mtx_write(path, size, rows, cols, vals, binary=False, index32=False, value32=False, array=False):
     r, c = np.ascontiguousarray(rows, dtype=np.int64), np.ascontiguousarray(cols, dtype=np.int64)
     v = np.ascontiguousarray(vals, dtype=np.float64)
-    rc = ref().ref_mtx_write(str(path).encode(), int(binary), i64(size[0]), i64(size[1]), i64(len(v)), P(r), P(c), P(v),
+    rc = ref().ref_mtx_write(str(path).encode(), 2 if array else int(binary), i64(size[0]), i64(size[1]), i64(len(v)), P(r), P(c), P(v),
                              int(index32), int(value32))
     if rc:
         raise RuntimeError(f"reference writer failed ({rc})")

@@ -477,10 +477,10 @@ int mtx_write_impl(const char* path, int format, int64_t n_rows, int64_t n_cols,
     auto fill = [&](auto& data) {
         for (int64_t i = 0; i < nnz; ++i) data.nonzeros.emplace_back(rows[i], cols[i], vals[i]);
     };
-    if (format == 0) {
+    if (format == 0 || format == 2) {
         gko::matrix_data<double, gko::int64> d(gko::dim<2>(n_rows, n_cols));
         fill(d);
-        gko::write_raw(out, d, gko::layout_type::coordinate);
+        gko::write_raw(out, d, format == 0 ? gko::layout_type::coordinate : gko::layout_type::array);
     } else if (index32 && value32) {
         gko::matrix_data<float, gko::int32> d(gko::dim<2>(n_rows, n_cols));
         fill(d);

@@ -293,6 +293,22 @@ int write_file(const char* path, int format, int precision, int64_t n_rows, int6
         for (int64_t i = 0; i < nnz; ++i)
             std::fprintf(f, "%lld %lld %.*g\n", static_cast<long long>(rows[i]) + 1, static_cast<long long>(cols[i]) + 1,
                          precision, static_cast<double>(vals[i]));
+    } else if (format == 2) {   // array real general: column-major, zeros filled in (mtx_io.cpp:627-655)
+        if (precision <= 0) precision = 6;
+        std::vector<int64_t> perm(static_cast<size_t>(nnz));
+        std::iota(perm.begin(), perm.end(), int64_t(0));
+        std::stable_sort(perm.begin(), perm.end(), [&](int64_t a, int64_t b) {
+            return cols[a] != cols[b] ? cols[a] < cols[b] : rows[a] < rows[b];
+        });
+        std::fprintf(f, "%%%%MatrixMarket matrix array real general\n%lld %lld\n", static_cast<long long>(n_rows),
+                     static_cast<long long>(n_cols));
+        size_t pos = 0;
+        for (int64_t j = 0; j < n_cols; ++j)
+            for (int64_t i = 0; i < n_rows; ++i) {
+                double v = 0.0;
+                if (pos < perm.size() && rows[perm[pos]] == i && cols[perm[pos]] == j) v = static_cast<double>(vals[perm[pos++]]);
+                std::fprintf(f, "%.*g\n", precision, v);
+            }
     } else {
         std::fclose(f);
         return GKOB200_EUNSUPPORTED;

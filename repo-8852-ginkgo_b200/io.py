@@ -10,7 +10,7 @@ import numpy as np
 from . import lib
 from .core import Error
 
-COORDINATE, BINARY = 0, 1
+COORDINATE, BINARY, ARRAY = 0, 1, 2
 
 
 def _check(rc, what):

@@ -126,6 +126,21 @@ def test_text_writer_matches_reference_bytes(gko, tmp_path):
     assert np.array_equal(r, rows[order]) and np.array_equal(c, cols[order]) and np.array_equal(v, vals[order])
 
 
+@needs_ref
+def test_array_writer_matches_reference_bytes(gko, tmp_path):
+    """gko::write of a Dense (array layout): column-major with explicit zeros."""
+    rng = np.random.default_rng(4)
+    key = rng.choice(7 * 5, 12, replace=False)
+    rows, cols, vals = key // 5, key % 5, rng.standard_normal(12)
+    pr, po = tmp_path / "ref.mtx", tmp_path / "ours.mtx"
+    oracle.ref_mtx_write(pr, (7, 5), rows, cols, vals, array=True)
+    gko.io.write_raw(po, (7, 5), rows.astype(np.int64), cols.astype(np.int64), vals, layout=gko.io.ARRAY)
+    assert po.read_text() == pr.read_text()
+    size, r, c, v = gko.io.read_raw(po, index_dtype=np.int64)
+    assert size == (7, 5) and len(v) == 35          # the array layout reads every entry back, zeros included
+    same((size, r, c, v), oracle.ref_mtx_read(po))
+
+
 @pytest.mark.parametrize("text,needle", [
     ("%%MatrixMarket matrix coordinate complex general\n1 1 1\n1 1 1.0 2.0\n", "complex"),
     ("%%MatrixMarket tensor coordinate real general\n1 1 1\n1 1 1.0\n", "header"),
