@@ -55,6 +55,29 @@ CG_SOLVE_KATS += [
      [[33.0], [-56.0], [81.0], [-30.0], [21.0], [40.0]], 100, 1e2),
 ]
 
+# fcg_kernels.cpp: the same fixtures as CG (mtx :62-64, mtx_big :77-84); SolvesStencilSystem :268-280,
+# SolvesMultipleStencilSystems :340-356, SolvesBigDenseSystem1/2 :460-475 / :494-509 (tolerance r*1e3)
+FCG_SOLVE_KATS = [(n, A, b, x, it, 1e3 if "Big" in n else t) for (n, A, b, x, it, t) in CG_SOLVE_KATS]
+# cgs_kernels.cpp: mtx :63-64, SolvesDenseSystem :319-331 (40 iterations, r), SolvesMultipleDenseSystem
+# :391-408, mtx_big :76-82, SolvesBigDenseSystem1 :513-527 (r*1e3), SolvesBigDenseSystem2 :545-559 (r*1e2)
+CGS_DENSE3 = [[1.0, -3.0, 0.0], [-4.0, 1.0, -3.0], [2.0, -1.0, 2.0]]
+CGS_BIG6 = [[-99.0, 87.0, -67.0, -62.0, -68.0, -19.0],
+            [-30.0, -17.0, -1.0, 9.0, 23.0, 77.0],
+            [80.0, 89.0, 36.0, 94.0, 55.0, 34.0],
+            [-31.0, 21.0, 96.0, -26.0, 24.0, -57.0],
+            [60.0, 45.0, -16.0, -4.0, 96.0, 24.0],
+            [69.0, 32.0, -68.0, 57.0, -30.0, -51.0]]
+CGS_SOLVE_KATS = [
+    ("SolvesDenseSystem", CGS_DENSE3, [[-1.0], [3.0], [1.0]], [[-4.0], [-1.0], [4.0]], 40, 1.0),
+    # (tolerance of this one: half_tol = sqrt(r), encoded as 0)
+    ("SolvesMultipleDenseSystem", CGS_DENSE3, [[-1.0, -5.0], [3.0, 1.0], [1.0, -2.0]],
+     [[-4.0, 1.0], [-1.0, 2.0], [4.0, -1.0]], 40, 0.0),
+    ("SolvesBigDenseSystem1", CGS_BIG6, [[764.0], [-4032.0], [-11855.0], [7111.0], [-12765.0], [-4589.0]],
+     [[-13.0], [-49.0], [69.0], [-33.0], [-82.0], [-39.0]], 100, 1e3),
+    ("SolvesBigDenseSystem2", CGS_BIG6, [[17356.0], [5466.0], [748.0], [-456.0], [3434.0], [-7020.0]],
+     [[-58.0], [98.0], [-16.0], [-58.0], [2.0], [76.0]], 100, 1e2),
+]
+
 
 def rtol(dtype):
     """r<T>::value of the reference tests: 10 * eps (core/test/utils.hpp:213-219)."""

@@ -112,3 +112,17 @@ def test_solves_dense_system_kat(ora, solver):
     b = np.array([[-1.0], [3.0], [1.0]])
     x, it, _, stop = ora.krylov_solve(solver, rp, ci, va, b, np.zeros_like(b), max_iters=100, factor=kat.rtol(np.float64))
     assert kat.rel_frobenius(x, [[-4.0], [-1.0], [4.0]]) <= kat.rtol(np.float64) * 1e1
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("solver,case", [("fcg", c) for c in kat.FCG_SOLVE_KATS] + [("cgs", c) for c in kat.CGS_SOLVE_KATS],
+                         ids=lambda v: v if isinstance(v, str) else v[0])
+def test_fcg_cgs_reference_solve_kats(ora, dtype, solver, case):
+    """The literal systems of reference/test/solver/{fcg,cgs}_kernels.cpp with the factories'
+    criteria (Iteration(max) + ResidualNorm(r<T>::value)) and the tests' own tolerances."""
+    _, A, b, expect, max_iters, tol_mult = case
+    rp, ci, va, _ = kat.dense_to_csr(A, dtype)
+    b = np.array(b, dtype=dtype)
+    x, it, _, _ = ora.krylov_solve(solver, rp, ci, va, b, np.zeros_like(b), max_iters=max_iters, factor=kat.rtol(dtype))
+    tol = np.sqrt(kat.rtol(dtype)) if tol_mult == 0.0 else kat.rtol(dtype) * tol_mult
+    assert kat.rel_frobenius(x, expect) <= tol
