@@ -164,3 +164,20 @@ def test_bicgstab_fp32_hybrid(gko, exec_, ora):
     s.apply(gko.matrix.Dense.from_numpy(exec_, b), dx)
     assert abs(s.num_iterations - it_ref) <= 2
     assert np.abs(dx.to_numpy() - x_ref).max() <= 1e-3 * np.abs(x_ref).max()
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("kind,case", [("Fcg", c) for c in kat.FCG_SOLVE_KATS] + [("Cgs", c) for c in kat.CGS_SOLVE_KATS],
+                         ids=lambda v: v if isinstance(v, str) else v[0])
+def test_fcg_cgs_reference_solve_kats(gko, exec_, dtype, kind, case):
+    """reference/test/solver/{fcg,cgs}_kernels.cpp: the tests' literal systems, criteria and tolerances."""
+    _, Am, b, expect, max_iters, tol_mult = case
+    rp, ci, va, shape = kat.dense_to_csr(Am, dtype)
+    A = gko.matrix.Csr.from_arrays(exec_, shape, rp, ci, va, strategy="classical")
+    b = np.array(b, dtype=dtype)
+    s = build(gko, exec_, kind, A, max_iters, kat.rtol(dtype), nrhs=b.shape[1])
+    db = gko.matrix.Dense.from_numpy(exec_, b)
+    dx = gko.matrix.Dense.create(exec_, b.shape, db.t.dtype)
+    s.apply(db, dx)
+    tol = np.sqrt(kat.rtol(dtype)) if tol_mult == 0.0 else kat.rtol(dtype) * tol_mult
+    assert kat.rel_frobenius(dx.to_numpy(), expect) <= tol
