@@ -22,6 +22,10 @@
 #include <numeric>
 #include <string>
 #include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#include <parallel/algorithm>
+#endif
 
 #include "../../include/gko_b200.h"
 
@@ -80,6 +84,91 @@ struct Tokens {
     }
 };
 
+// ---- parallel token parsing ------------------------------------------------------------------
+// The body of a MatrixMarket file is a stream of whitespace-separated tokens (the reference reads
+// it with successive `stream >> x`, line structure does not matter).  The buffer is cut into
+// chunks at token boundaries, tokens are counted per chunk (pass 1), and every chunk then knows
+// the global index of its first token and parses its own tokens (pass 2): field = index % fields.
+inline bool is_space(char ch) { return std::isspace(static_cast<unsigned char>(ch)) != 0; }
+
+struct TokenTable {
+    std::vector<const char*> chunk_begin;   // first token start of every chunk (+ end sentinel)
+    std::vector<int64_t> first_index;       // global index of that token
+    int64_t total = 0;
+};
+
+TokenTable index_tokens(const char* begin, const char* end)
+{
+    int n_chunks = 1;
+#ifdef _OPENMP
+    n_chunks = omp_get_max_threads() * 4;
+#endif
+    const size_t len = static_cast<size_t>(end - begin);
+    if (len < (1u << 20)) n_chunks = 1;
+    TokenTable t;
+    t.chunk_begin.resize(n_chunks + 1);
+    t.first_index.assign(n_chunks + 1, 0);
+    for (int c = 0; c <= n_chunks; ++c) {
+        const char* p = begin + len * static_cast<size_t>(c) / n_chunks;
+        if (c == n_chunks) {
+            p = end;
+        } else if (p > begin) {
+            while (p < end && !is_space(p[-1])) ++p;   // finish the token the cut landed in
+        }
+        while (p < end && is_space(*p)) ++p;           // next token start
+        t.chunk_begin[c] = p;
+    }
+    std::vector<int64_t> count(n_chunks, 0);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int c = 0; c < n_chunks; ++c) {
+        int64_t k = 0;
+        const char* p = t.chunk_begin[c];
+        const char* e = t.chunk_begin[c + 1];
+        while (p < e) {
+            ++k;
+            while (p < e && !is_space(*p)) ++p;
+            while (p < e && is_space(*p)) ++p;
+        }
+        count[c] = k;
+    }
+    for (int c = 0; c < n_chunks; ++c) t.first_index[c + 1] = t.first_index[c] + count[c];
+    t.total = t.first_index[n_chunks];
+    return t;
+}
+
+// Parses the first n_entries * fields tokens: field f < int_fields as int64 into ints[f][entry],
+// the others as double into vals[entry].  Returns the index of the first entry that failed to
+// parse, or -1.
+int64_t parse_tokens(const TokenTable& t, int64_t n_entries, int fields, int int_fields, std::vector<int64_t>* ints,
+                     std::vector<double>& vals)
+{
+    int64_t bad = std::numeric_limits<int64_t>::max();
+    const int n_chunks = static_cast<int>(t.chunk_begin.size()) - 1;
+#pragma omp parallel for schedule(dynamic, 1) reduction(min : bad)
+    for (int c = 0; c < n_chunks; ++c) {
+        const char* p = t.chunk_begin[c];
+        const char* e = t.chunk_begin[c + 1];
+        int64_t g = t.first_index[c];
+        while (p < e && g < n_entries * fields) {
+            const int64_t entry = g / fields;
+            const int f = static_cast<int>(g % fields);
+            char* q = nullptr;
+            if (f < int_fields) {
+                ints[f][entry] = std::strtoll(p, &q, 10);
+            } else {
+                vals[entry] = std::strtod(p, &q);
+            }
+            // the token has to be consumed completely (`stream >> x` would leave the rest for the
+            // next extraction, which then fails)
+            if (q == p || (q < e && !is_space(*q))) bad = std::min(bad, entry);
+            while (p < e && !is_space(*p)) ++p;
+            while (p < e && is_space(*p)) ++p;
+            ++g;
+        }
+    }
+    return bad == std::numeric_limits<int64_t>::max() ? -1 : bad;
+}
+
 enum Layout { COORDINATE, ARRAY };
 enum Entry { REAL, INTEGER, COMPLEX, PATTERN };
 enum Modifier { GENERAL, SYMMETRIC, SKEW, HERMITIAN };
@@ -104,11 +193,20 @@ void insert(MtxData& d, Modifier m, int64_t r, int64_t c, double v)
 void sort_row_major(MtxData& d)
 {
     const size_t n = d.vals.size();
+    bool sorted = true;
+    for (size_t i = 1; i < n && sorted; ++i)
+        sorted = d.rows[i - 1] < d.rows[i] || (d.rows[i - 1] == d.rows[i] && d.cols[i - 1] <= d.cols[i]);
+    if (sorted) return;   // the usual case for files written by a library
     std::vector<size_t> perm(n);
     std::iota(perm.begin(), perm.end(), size_t(0));
-    std::stable_sort(perm.begin(), perm.end(), [&](size_t a, size_t b) {
+    auto less = [&](size_t a, size_t b) {
         return d.rows[a] != d.rows[b] ? d.rows[a] < d.rows[b] : d.cols[a] < d.cols[b];
-    });
+    };
+#ifdef _OPENMP
+    __gnu_parallel::stable_sort(perm.begin(), perm.end(), less);
+#else
+    std::stable_sort(perm.begin(), perm.end(), less);
+#endif
     MtxData s;
     s.rows.resize(n);
     s.cols.resize(n);
@@ -164,34 +262,51 @@ int read_text(const std::string& buf, MtxData& d)
         if (!getline(line)) return fail("error when reading the dimensions line");
     } while (!line.empty() && line[0] == '%');
     Tokens dims{line.data(), line.data() + line.size()};
-    Tokens body{buf.data() + pos, buf.data() + buf.size()};
     int64_t nnz = 0;
     if (!dims.next_i64(d.n_rows) || !dims.next_i64(d.n_cols) || d.n_rows < 0 || d.n_cols < 0)
         return fail("error when determining matrix size, expected: rows cols nnz");
+    const TokenTable tokens = index_tokens(buf.data() + pos, buf.data() + buf.size());
     if (layout == COORDINATE) {
         if (!dims.next_i64(nnz) || nnz < 0) return fail("error when determining matrix size, expected: rows cols nnz");
+        const int fields = entry == PATTERN ? 2 : 3;
+        std::vector<int64_t> ints[2];
+        std::vector<double> vals(static_cast<size_t>(nnz), 1.0);
+        // entries the file does not have tokens for fail like a stream at its end
+        const int64_t have = tokens.total / fields;
+        const int64_t n_parse = std::min(nnz, have);
+        ints[0].resize(static_cast<size_t>(nnz));
+        ints[1].resize(static_cast<size_t>(nnz));
+        const int64_t bad = parse_tokens(tokens, n_parse, fields, 2, ints, vals);
+        const int64_t first_bad = bad >= 0 ? bad : (have < nnz ? have : -1);
+        if (first_bad >= 0) {
+            // which extraction failed: the coordinates or the value
+            const bool coord_missing = bad < 0 && tokens.total - have * fields < 2;
+            return fail((bad >= 0 || coord_missing ? "error when reading coordinates of matrix entry "
+                                                   : "error when reading matrix entry ") +
+                        std::to_string(first_bad));
+        }
         const size_t reserve = static_cast<size_t>(mod == GENERAL ? nnz : 2 * nnz);
         d.rows.reserve(reserve);
         d.cols.reserve(reserve);
         d.vals.reserve(reserve);
-        for (int64_t i = 0; i < nnz; ++i) {
-            int64_t r, c;
-            double v = 1.0;
-            if (!body.next_i64(r) || !body.next_i64(c))
-                return fail("error when reading coordinates of matrix entry " + std::to_string(i));
-            if (entry != PATTERN && !body.next_f64(v)) return fail("error when reading matrix entry " + std::to_string(i));
-            insert(d, mod, r - 1, c - 1, v);
-        }
+        for (int64_t i = 0; i < nnz; ++i) insert(d, mod, ints[0][i] - 1, ints[1][i] - 1, vals[i]);
     } else {
-        if (entry == PATTERN) return fail("array layout cannot hold a pattern matrix");
+        int64_t count = 0;
         for (int64_t c = 0; c < d.n_cols; ++c) {
             const int64_t start = mod == GENERAL ? 0 : mod == SKEW ? c + 1 : c;
-            for (int64_t r = start; r < d.n_rows; ++r) {
-                double v;
-                if (!body.next_f64(v))
-                    return fail("error when reading matrix entry " + std::to_string(r) + " ," + std::to_string(c));
-                insert(d, mod, r, c, v);
-            }
+            count += std::max<int64_t>(0, d.n_rows - start);
+        }
+        std::vector<double> vals(static_cast<size_t>(count), 1.0);   // pattern entries are ones and read nothing
+        if (entry != PATTERN) {
+            const int64_t n_parse = std::min(count, tokens.total);
+            const int64_t bad = parse_tokens(tokens, n_parse, 1, 0, nullptr, vals);
+            const int64_t first_bad = bad >= 0 ? bad : (tokens.total < count ? tokens.total : -1);
+            if (first_bad >= 0) return fail("error when reading matrix entry " + std::to_string(first_bad));
+        }
+        int64_t k = 0;
+        for (int64_t c = 0; c < d.n_cols; ++c) {
+            const int64_t start = mod == GENERAL ? 0 : mod == SKEW ? c + 1 : c;
+            for (int64_t r = start; r < d.n_rows; ++r) insert(d, mod, r, c, vals[k++]);
         }
     }
     sort_row_major(d);

@@ -86,6 +86,33 @@ def test_random_coordinate_files_match_reference(gko, tmp_path, modifier, entry)
 
 
 @needs_ref
+@pytest.mark.parametrize("entry", ["real", "pattern"])
+def test_large_file_with_free_token_layout(gko, tmp_path, entry):
+    """> 1 MB: the parallel parser cuts the body at token boundaries.  The grammar is a token
+    stream — several entries per line, entries split across lines, tabs, blank lines — and the
+    entries arrive unsorted."""
+    rng = np.random.default_rng(11)
+    n, nnz = 5000, 150_000
+    key = rng.choice(n * n, nnz, replace=False)
+    toks = []
+    for k in key:
+        toks += [str(k // n + 1), str(k % n + 1)] + ([] if entry == "pattern" else [f"{rng.standard_normal():.17g}"])
+    seps = rng.choice([" ", "\n", "\t", "  ", "\n\n", " \n"], len(toks))
+    body = "".join(t + s for t, s in zip(toks, seps))
+    p = tmp_path / "big.mtx"
+    p.write_text(f"%%MatrixMarket matrix coordinate {entry} general\n%c\n{n} {n} {nnz}\n" + body + "\n")
+    assert p.stat().st_size > (1 << 20)
+    same(gko.io.read_raw(p, index_dtype=np.int64), oracle.ref_mtx_read(p))
+    # truncated in the middle of an entry: both readers fail
+    q = tmp_path / "cut.mtx"
+    q.write_text(p.read_text()[: p.stat().st_size * 2 // 3])
+    with pytest.raises(gko.Error):
+        gko.io.read_raw(q)
+    with pytest.raises(RuntimeError):
+        oracle.ref_mtx_read(q)
+
+
+@needs_ref
 @pytest.mark.parametrize("index32", [True, False])
 @pytest.mark.parametrize("value32", [True, False])
 def test_binary_files_both_directions(gko, tmp_path, index32, value32):
