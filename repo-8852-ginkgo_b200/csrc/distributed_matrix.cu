@@ -692,6 +692,10 @@ int gkob200_dist_solver_create(int kind, gkob200_dist_matrix* A, const gkob200_p
     if (!A || !stop || !out) return GKOB200_EINVAL;
     *out = nullptr;
     if (kind != GKOB200_SOLVER_CG) return GKOB200_EUNSUPPORTED;
+    gkob200_stop clamped = *stop;
+    if (clamped.max_iters < 0) clamped.max_iters = 0;
+    if (clamped.max_iters > (int64_t(1) << 40)) clamped.max_iters = int64_t(1) << 40;
+    stop = &clamped;
     int rc;
     if (A->local.value_type == GKOB200_F64) {
         auto* s = new DistCgSolver<double>();

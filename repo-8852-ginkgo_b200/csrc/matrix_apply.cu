@@ -172,6 +172,11 @@ int gkob200_solver_create(int kind, const gkob200_matrix* A, const gkob200_preco
 {
     if (!A || !stop || !out || nrhs < 1) return GKOB200_EINVAL;
     *out = nullptr;
+    // iteration limits are clamped so that `max_iters + chunk` style arithmetic cannot overflow
+    gkob200_stop clamped = *stop;
+    if (clamped.max_iters < 0) clamped.max_iters = 0;
+    if (clamped.max_iters > (int64_t(1) << 40)) clamped.max_iters = int64_t(1) << 40;
+    stop = &clamped;
     int rc = GKOB200_EUNSUPPORTED;
     gkob200_solver* s = nullptr;
     if (kind == GKOB200_SOLVER_CG) {

@@ -19,6 +19,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <new>
+#include <stdexcept>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -270,12 +272,13 @@ int read_text(const std::string& buf, MtxData& d)
         if (!dims.next_i64(nnz) || nnz < 0) return fail("error when determining matrix size, expected: rows cols nnz");
         const int fields = entry == PATTERN ? 2 : 3;
         std::vector<int64_t> ints[2];
-        std::vector<double> vals(static_cast<size_t>(nnz), 1.0);
-        // entries the file does not have tokens for fail like a stream at its end
+        // entries the file does not have tokens for fail like a stream at its end; the header's
+        // nnz is not trusted for allocation: at most `have` entries (bounded by the file size)
         const int64_t have = tokens.total / fields;
         const int64_t n_parse = std::min(nnz, have);
-        ints[0].resize(static_cast<size_t>(nnz));
-        ints[1].resize(static_cast<size_t>(nnz));
+        std::vector<double> vals(static_cast<size_t>(n_parse), 1.0);
+        ints[0].resize(static_cast<size_t>(n_parse));
+        ints[1].resize(static_cast<size_t>(n_parse));
         const int64_t bad = parse_tokens(tokens, n_parse, fields, 2, ints, vals);
         const int64_t first_bad = bad >= 0 ? bad : (have < nnz ? have : -1);
         if (first_bad >= 0) {
@@ -289,12 +292,25 @@ int read_text(const std::string& buf, MtxData& d)
         d.rows.reserve(reserve);
         d.cols.reserve(reserve);
         d.vals.reserve(reserve);
-        for (int64_t i = 0; i < nnz; ++i) insert(d, mod, ints[0][i] - 1, ints[1][i] - 1, vals[i]);
+        for (int64_t i = 0; i < nnz; ++i) {
+            // coordinates feed device assembly: they must address the declared matrix
+            if (ints[0][i] < 1 || ints[0][i] > d.n_rows || ints[1][i] < 1 || ints[1][i] > d.n_cols)
+                return fail("matrix entry " + std::to_string(i) + " lies outside of the " + std::to_string(d.n_rows) +
+                            " x " + std::to_string(d.n_cols) + " matrix");
+            insert(d, mod, ints[0][i] - 1, ints[1][i] - 1, vals[i]);
+        }
     } else {
         int64_t count = 0;
         for (int64_t c = 0; c < d.n_cols; ++c) {
             const int64_t start = mod == GENERAL ? 0 : mod == SKEW ? c + 1 : c;
             count += std::max<int64_t>(0, d.n_rows - start);
+        }
+        if (entry != PATTERN && tokens.total < count) {
+            // fewer values than the dimensions ask for: fail at the first missing (or malformed)
+            // one without allocating what the header claims
+            std::vector<double> part(static_cast<size_t>(tokens.total), 1.0);
+            const int64_t bad = parse_tokens(tokens, tokens.total, 1, 0, nullptr, part);
+            return fail("error when reading matrix entry " + std::to_string(bad >= 0 ? bad : tokens.total));
         }
         std::vector<double> vals(static_cast<size_t>(count), 1.0);   // pattern entries are ones and read nothing
         if (entry != PATTERN) {
@@ -339,7 +355,10 @@ int read_binary(const std::string& buf, MtxData& d)
     if (vb == 'Z' || vb == 'C') return fail("cannot read into this format, would assign complex to real");
     const size_t isz = ib == 'I' ? 4 : 8, vsz = vb == 'D' ? 8 : 4, rec = 2 * isz + vsz;
     const uint64_t n = hdr[3];
-    if (buf.size() < 32 + n * rec) return fail("failed reading entry " + std::to_string((buf.size() - 32) / rec));
+    // (checked: 32 + n * rec can wrap for a hostile n)
+    if (n > (buf.size() - 32) / rec) return fail("failed reading entry " + std::to_string((buf.size() - 32) / rec));
+    if (hdr[1] > static_cast<uint64_t>(INT64_MAX) || hdr[2] > static_cast<uint64_t>(INT64_MAX))
+        return fail("invalid matrix dimensions in the header");
     d.n_rows = static_cast<int64_t>(hdr[1]);
     d.n_cols = static_cast<int64_t>(hdr[2]);
     d.rows.resize(n);
@@ -365,6 +384,10 @@ int read_binary(const std::string& buf, MtxData& d)
             d.vals[i] = v;
         }
     }
+    for (uint64_t i = 0; i < n; ++i)
+        if (d.rows[i] < 0 || d.rows[i] >= d.n_rows || d.cols[i] < 0 || d.cols[i] >= d.n_cols)
+            return fail("matrix entry " + std::to_string(i) + " lies outside of the " + std::to_string(d.n_rows) +
+                        " x " + std::to_string(d.n_cols) + " matrix");
     sort_row_major(d);
     return 0;
 }
@@ -443,11 +466,21 @@ int gkob200_mtx_read_open(const char* path, void** handle, int64_t* n_rows, int6
     if (!path || !handle || !n_rows || !n_cols || !nnz) return GKOB200_EINVAL;
     *handle = nullptr;
     std::string buf;
-    if (!read_file(path, buf)) return fail(std::string("failed reading from stream: ") + path);
+    try {
+        if (!read_file(path, buf)) return fail(std::string("failed reading from stream: ") + path);
+    } catch (const std::exception& e) {
+        return fail(std::string("failed reading from stream: ") + e.what());
+    }
     if (buf.empty()) return fail("failed reading from stream");
-    auto* d = new MtxData();
+    auto* d = new (std::nothrow) MtxData();
+    if (!d) return fail("out of memory");
     // read_generic_raw: a '%' first byte selects the text reader (mtx_io.cpp:911-925)
-    const int rc = buf[0] == '%' ? read_text(buf, *d) : read_binary(buf, *d);
+    int rc;
+    try {   // nothing may propagate through the C boundary (bad_alloc / length_error on hostile sizes)
+        rc = buf[0] == '%' ? read_text(buf, *d) : read_binary(buf, *d);
+    } catch (const std::exception& e) {
+        rc = fail(std::string("cannot hold the matrix described by the file: ") + e.what());
+    }
     if (rc) {
         delete d;
         return rc;
@@ -470,7 +503,13 @@ int gkob200_mtx_read_close(void* handle)
     { return copy_out<VT, IT>(static_cast<const MtxData*>(handle), rows, cols, vals); }                              \
     int gkob200_mtx_write_##V##_##I(const char* path, int format, int precision, int64_t n_rows, int64_t n_cols,     \
                                     int64_t nnz, const IT* rows, const IT* cols, const VT* vals)                     \
-    { return write_file<VT, IT>(path, format, precision, n_rows, n_cols, nnz, rows, cols, vals); }
+    {                                                                                                                \
+        try {                                                                                                        \
+            return write_file<VT, IT>(path, format, precision, n_rows, n_cols, nnz, rows, cols, vals);              \
+        } catch (const std::exception& e) {                                                                          \
+            return fail(std::string("error when writing matrix data: ") + e.what());                                \
+        }                                                                                                            \
+    }
 GKOB200_DEF_MTX(f64, double, i32, int32_t)
 GKOB200_DEF_MTX(f32, float, i32, int32_t)
 GKOB200_DEF_MTX(f64, double, i64, int64_t)

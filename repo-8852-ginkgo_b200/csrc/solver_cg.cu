@@ -143,8 +143,9 @@ __global__ void cg_criterion_k(SolverState* st, int64_t k, const V* tau, const V
 }
 
 template <typename V>
-__global__ void init_state(SolverState* st, V* sc, int64_t k)
+__global__ void init_state(SolverState* st, V* sc, int64_t k, int hist_cap)
 {
+    st->hist_cap = hist_cap;
     st->stopped = 0;
     st->iter = 0;
     st->final_iter = 0;
@@ -192,8 +193,7 @@ struct CgSolver : gkob200_solver {
         if ((rc = scalars.alloc(static_cast<size_t>(S_COUNT) * k * sizeof(V)))) return rc;
         if ((rc = state.alloc(sizeof(SolverState)))) return rc;
         if ((rc = status.alloc(static_cast<size_t>(k) + 16))) return rc;
-        const int64_t hist_len = stop.max_iters + 2 < (int64_t(1) << 24) ? stop.max_iters + 2 : (int64_t(1) << 24);
-        if ((rc = hist.alloc(static_cast<size_t>(hist_len) * sizeof(V)))) return rc;
+        if ((rc = hist.alloc(static_cast<size_t>(history_capacity(stop.max_iters)) * sizeof(V)))) return rc;
         // reduction scratch: room for one partial per CTA of the largest grid any fused
         // kernel launches (the SpMV with the fused dot runs one CTA per 128 rows)
         ws_blocks = ceildiv(n, 128) + 1;
@@ -332,7 +332,7 @@ struct CgSolver : gkob200_solver {
         int rc;
         SolverState* st = state.as<SolverState>();
         // ---- prologue: initialize, r = b - A x, criterion baseline ----------
-        init_state<V><<<1, 1, 0, s>>>(st, scalars.as<V>(), k);
+        init_state<V><<<1, 1, 0, s>>>(st, scalars.as<V>(), k, static_cast<int>(hist.bytes / sizeof(V)));
         if ((rc = gkob200_cg_initialize_f(s, b, bs))) return rc;
         launch_count += 3;
         if ((rc = matrix_apply<V>(s, A, x, 1, 1, sc(S_NEG_ONE), sc(S_ONE), r(), 1, nullptr))) return rc;
@@ -523,7 +523,7 @@ int CgSolver<V>::apply_general(cudaStream_t s, const V* b, int64_t bs, V* x, int
     int rc;
     SolverState* st = state.as<SolverState>();
     uint8_t* stat = status.as<uint8_t>();
-    init_state<V><<<1, 1, 0, s>>>(st, scalars.as<V>(), k);
+    init_state<V><<<1, 1, 0, s>>>(st, scalars.as<V>(), k, static_cast<int>(hist.bytes / sizeof(V)));
     if ((rc = gkob200_cg_initialize_f(s, b, bs))) return rc;
     if ((rc = matrix_apply<V>(s, A, x, xs, k, sc(S_NEG_ONE), sc(S_ONE), r(), k, nullptr))) return rc;
     if ((rc = baseline_norm(s, b, bs))) return rc;

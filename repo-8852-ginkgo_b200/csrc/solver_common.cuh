@@ -14,7 +14,17 @@ struct SolverState {
     int iter;        // the reference's `iter` (number of completed iterations)
     int final_iter;  // value of `iter` when the solver stopped
     int one_changed; // last criterion check changed at least one column (BiCGSTAB finalize)
+    int hist_cap;    // entries the residual-history buffer holds (writes beyond it are dropped)
 };
+
+// Residual-history length for a solver: every iteration when an Iteration criterion bounds
+// the solve, a fixed 64 Ki window otherwise (stop.py passes max_iters = 2^31-2 for "no
+// Iteration criterion"; the history of such a solve is truncated, never overrun).
+inline int64_t history_capacity(int64_t max_iters)
+{
+    if (max_iters < 0) max_iters = 0;
+    return max_iters <= (int64_t(1) << 20) ? max_iters + 2 : (int64_t(1) << 16);
+}
 
 // What stop::Combined{Iteration(max_iters), ResidualNorm(factor, baseline)} does in
 // one check [ref: core/stop/combined.cpp:40-58, iteration.cpp:40-51,
@@ -32,7 +42,7 @@ __device__ __forceinline__ void criterion_check(SolverState* st, int64_t k, cons
     // st->iter is what the reference's `iter` becomes at its next "++iter"; a check that
     // does not start a new iteration (BiCGSTAB's mid-iteration check) sees the current one
     const int it = advance ? st->iter : st->iter - 1;
-    if (hist && advance) hist[it] = tau[0];
+    if (hist && advance && it < st->hist_cap) hist[it] = tau[0];
     bool one_changed = false, all = false;
     // criterion 1: Iteration
     if (it >= max_iters) {
@@ -160,8 +170,9 @@ __global__ void criterion_kernel(SolverState* st, int64_t k, const V* tau, const
 }
 
 template <typename V>
-__global__ void init_state_kernel(SolverState* st, V* one, V* neg_one, int64_t k)
+__global__ void init_state_kernel(SolverState* st, V* one, V* neg_one, int64_t k, int hist_cap)
 {
+    st->hist_cap = hist_cap;
     st->stopped = 0;
     st->iter = 0;
     st->final_iter = 0;
@@ -207,8 +218,7 @@ struct SolverBase : gkob200_solver {
         if ((rc = status.alloc(static_cast<size_t>(k) + 16))) return rc;
         if ((rc = consts.alloc(2 * k * sizeof(V)))) return rc;
         if ((rc = taus.alloc(2 * k * sizeof(V)))) return rc;
-        const int64_t hist_len = stop.max_iters + 2 < (int64_t(1) << 24) ? stop.max_iters + 2 : (int64_t(1) << 24);
-        if ((rc = hist.alloc(static_cast<size_t>(hist_len) * sizeof(V)))) return rc;
+        if ((rc = hist.alloc(static_cast<size_t>(history_capacity(stop.max_iters)) * sizeof(V)))) return rc;
         if ((rc = ws.alloc(GKOB200_REDUCE_WS_BYTES))) return rc;
         GKOB200_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h_state), 2 * sizeof(SolverState), cudaHostAllocDefault));
         stop_status_host.assign(k, 0);
@@ -217,7 +227,7 @@ struct SolverBase : gkob200_solver {
 
     int reset_state(cudaStream_t s)
     {
-        init_state_kernel<V><<<1, 1, 0, s>>>(st(), one(), neg_one(), k);
+        init_state_kernel<V><<<1, 1, 0, s>>>(st(), one(), neg_one(), k, static_cast<int>(hist.bytes / sizeof(V)));
         ++launch_count;
         GKOB200_CHECK_LAUNCH();
         return 0;

@@ -847,12 +847,18 @@ void apply(Exec, size_type num_blocks, uint32, const preconditioner::block_inter
 }
 void initialize_precisions(Exec exec, const array<precision_reduction>& source, array<precision_reduction>& precisions)
 {
-    // full precision only on this path: every entry is the (1-byte) source pattern repeated
+    // Blocks are stored in full precision only on this path.  A request for reduced or
+    // autodetected storage (adaptive-precision Jacobi, core/preconditioner/jacobi_utils.hpp:45-70)
+    // is refused loudly: storing full-precision blocks under metadata that says "reduced" would
+    // make every later decode / convert / transpose of the preconditioner wrong.
     const auto n = precisions.get_num_elems();
     const auto m = source.get_num_elems();
     array<precision_reduction> host_src(exec->get_master(), source);
+    for (size_type i = 0; i < m; ++i)
+        if (!(host_src.get_const_data()[i] == precision_reduction(0, 0)))
+            throw NotSupported(__FILE__, __LINE__, __func__, "adaptive-precision block-Jacobi storage");
     array<precision_reduction> host_dst(exec->get_master(), n);
-    for (size_type i = 0; i < n; ++i) host_dst.get_data()[i] = host_src.get_const_data()[i % m];
+    for (size_type i = 0; i < n; ++i) host_dst.get_data()[i] = precision_reduction(0, 0);
     precisions = host_dst;
 }
 #define INST_JAC(V)                                                                                             \

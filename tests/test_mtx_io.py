@@ -196,3 +196,32 @@ def test_index_overflow_is_rejected(gko, tmp_path):
         gko.io.read_raw(p, index_dtype=np.int32)
     size, r, c, v = gko.io.read_raw(p, index_dtype=np.int64)
     assert size == (3000000000, 5) and r.tolist() == [2999999998]
+
+
+def _binary(n_rows, n_cols, nnz_header, triplets):
+    import struct
+    out = b"GINKGODI" + struct.pack("<QQQ", n_rows, n_cols, nnz_header)
+    for r, c, v in triplets:
+        out += struct.pack("<iid", r, c, v)
+    return out
+
+
+@pytest.mark.parametrize("payload,needle", [
+    # header sizes are not trusted: a huge nnz with a tiny body fails at the first missing entry
+    (b"%%MatrixMarket matrix coordinate real general\n2 2 4000000000000\n1 1 1.0\n", "entry 1"),
+    (b"%%MatrixMarket matrix array real general\n3000000 3000000\n1.0\n", "entry 1"),
+    # coordinates outside the declared matrix must never reach device assembly
+    (b"%%MatrixMarket matrix coordinate real general\n2 2 2\n1 1 1.0\n3 1 2.0\n", "outside"),
+    (b"%%MatrixMarket matrix coordinate real general\n2 2 1\n0 1 1.0\n", "outside"),
+    (b"%%MatrixMarket matrix coordinate pattern general\n2 2 1\n1 5\n", "outside"),
+    # binary: 32 + n * rec wraps around 2^64 for this n; and out-of-range entries
+    (_binary(2, 2, (2 ** 64) // 16 + 1, [(0, 0, 1.0)]), "entry"),
+    (_binary(2, 2, 1, [(2, 0, 1.0)]), "outside"),
+    (_binary(2, 2, 1, [(0, -1, 1.0)]), "outside"),
+])
+def test_hostile_sizes_and_coordinates_fail_cleanly(gko, tmp_path, payload, needle):
+    p = tmp_path / "hostile.mtx"
+    p.write_bytes(payload)
+    with pytest.raises(gko.Error) as e:
+        gko.io.read_raw(p)
+    assert needle in str(e.value)
