@@ -43,7 +43,17 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--grid", type=int, default=200, help="stencil grid edge per GPU (200 -> configs[1])")
+    ap.add_argument("--grid", type=int, default=None,
+                    help="stencil grid edge (default 200 at N=1 -> configs[1]; 512 at N>1 -> configs[3])")
+    ap.add_argument("--stencil", default=None, choices=["7pt", "27pt"], help="N>1 only (default 7pt -> configs[3])")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1: weak = one grid x grid x (grid/8) slab per GPU, strong = grid^3 fixed")
+    ap.add_argument("--slab-planes", type=int, default=None, help="weak scaling: planes per GPU (default grid/8)")
+    ap.add_argument("--dist-precond", default="none", choices=["none", "jacobi"])
+    ap.add_argument("--dist", action="store_true", help="run the distributed bench also at N=1 (strong-scaling base)")
+    ap.add_argument("--no-verify", action="store_true", help="N>1: skip the parity checks outside the timed region")
+    ap.add_argument("--verify-full", action="store_true",
+                    help="N>1: also compare the full-size residual norms with a single-GPU solve of the global system")
     ap.add_argument("--iters-per-step", type=int, default=100)
     ap.add_argument("--ref-iters-per-step", type=int, default=4)
     ap.add_argument("--cpu-baseline-iters", type=int, default=8)
@@ -119,32 +129,60 @@ def cg_model_bytes(n, nnz, precond_bytes, v=8, i=4):
     return 18 * n * v + nnz * (v + i) + (n + 1) * i + precond_bytes
 
 
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def run_reference(args, rank, world):
-    """The reference's own CPU implementation (OpenMP executor, all host threads)."""
+    """The reference's own CPU implementation (Ginkgo OpenMP executor from oracle/_ref, all host
+    threads) on this arm's workload.  N=1: configs[1] (CG + scalar Jacobi, 27-pt 200^3).  N>1:
+    configs[3] — the reference's distributed classes need MPI (not in this image), so the CPU
+    arm solves the same GLOBAL system (all N slabs) with its non-distributed CG; the arithmetic
+    is the same, and `value` uses the same definition as the GPU arm (iterations/s x N slabs for
+    weak scaling).  The matrix comes from the oracle's own generator: the product library is
+    never loaded in this process.  Rank 0 alone runs; torchrun's OMP_NUM_THREADS=1 is overridden."""
     if rank != 0:
         return
     import oracle
-    from __graft_entry__ import load_package
-    gko = load_package()  # host generators only (no GPU work)
-    g = args.grid
-    rp, ci, va, n = gko.gen.stencil_csr("27pt", g, g, g)
+    cores = host_threads()
+    dist_cfg = args.gpus > 1 or args.dist
+    if dist_cfg:
+        kind, g = args.stencil or "7pt", args.grid or 512
+        planes = args.slab_planes or max(g // 8, 1)
+        nz = planes * args.gpus if args.scaling == "weak" else g
+        nx = ny = g
+        precond_block = 1 if args.dist_precond == "jacobi" else 0
+        slabs = args.gpus if args.scaling == "weak" else 1
+        workload = (f"CG ({'scalar Jacobi' if precond_block else 'no preconditioner'}), 3D {kind} stencil "
+                    f"{nx}x{ny}x{nz} (the global system of BASELINE configs[3] at {args.gpus} GPUs, {args.scaling} "
+                    "scaling), fp64/int32 CSR, one host")
+    else:
+        kind, g = "27pt", args.grid or 200
+        nx = ny = nz = g
+        precond_block, slabs = 1, 1
+        workload = f"CG + scalar Jacobi, 3D 27-pt stencil {g}^3, fp64/int32 CSR (BASELINE configs[1])"
+    rp, ci, va, n = oracle.gen_stencil_csr(kind, nx, ny, nz)
     b = np.ones(n)
     it_per = args.ref_iters_per_step
     if oracle.ref() is not None:
-        kind, cores = "reference", oracle.ref_threads()
+        oracle.ref().ref_set_num_threads(cores)
+        kind_, cores = "reference", oracle.ref_threads()
 
         def step():
-            _, it, _, secs = oracle.ref_solve(rp, ci, va, b, np.zeros(n), precond_block=1, max_iters=it_per,
+            _, it, _, secs = oracle.ref_solve(rp, ci, va, b, np.zeros(n), precond_block=precond_block, max_iters=it_per,
                                               factor=0.0, omp=True, want_hist=False)
             return it, secs
     else:
-        kind, cores = "port", 1
-        inv = 1.0 / np.full(n, 26.0)
+        kind_, cores = "port", 1
+        inv = 1.0 / np.full(n, STENCIL_DIAG_REF[kind])
 
         def step():
             t0 = time.perf_counter()
-            _, it, _, _ = oracle.cg_solve(rp, ci, va, b, np.zeros(n), precond=1, inv_diag=inv, max_iters=it_per,
-                                          factor=0.0)
+            _, it, _, _ = oracle.cg_solve(rp, ci, va, b, np.zeros(n), precond=precond_block, inv_diag=inv,
+                                          max_iters=it_per, factor=0.0)
             return it, time.perf_counter() - t0
     for _ in range(args.warmup):
         step()
@@ -153,19 +191,23 @@ def run_reference(args, rank, world):
         it, s = step()
         total_it += it
         total_s += s
-    value = total_it / total_s
-    sample = f"27-pt {g}^3 fp64 CSR, CG + scalar Jacobi, {it_per} iterations per step on the host"
+    value = slabs * total_it / total_s
+    sample = f"{workload}; {it_per} iterations per step on the host"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"CG + scalar Jacobi, 3D 27-pt stencil {g}^3, fp64/int32 CSR (BASELINE configs[1])",
-                   "rows": n, "nnz": int(len(ci)), "iters_per_step": it_per},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "higher_is_better": True, "scaling": args.scaling if dist_cfg else "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload, "rows": n, "nnz": int(len(ci)), "iters_per_step": it_per,
+                   "value_definition": "CG iterations/s x N slabs" if slabs > 1 else "CG iterations/s"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind_, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+STENCIL_DIAG_REF = {"7pt": 6.0, "27pt": 26.0}
 
 
 def ncu_traffic(fmt, grid):
@@ -191,13 +233,16 @@ def main():
     import torch.distributed as dist
     from __graft_entry__ import load_package
     gko = load_package()
-    if world > 1:
+    if world > 1 or args.dist:
+        if world == 1:   # not under torchrun: a one-rank process group
+            for k, v in (("MASTER_ADDR", "127.0.0.1"), ("MASTER_PORT", "29555"), ("RANK", "0"), ("WORLD_SIZE", "1")):
+                os.environ.setdefault(k, v)
         from bench_dist import run_distributed
         run_distributed(args, gko, rank, world, local_rank)
         return
 
     exec_ = gko.CudaExecutor.create(local_rank)
-    g = args.grid
+    g = args.grid or 200
     rp, ci, va, n = gko.gen.stencil_csr("27pt", g, g, g)
     nnz = int(len(ci))
     A = gko.matrix.Csr.from_arrays(exec_, (n, n), rp, ci, va)
@@ -297,10 +342,11 @@ def main():
 
 def cpu_baseline(args, rp, ci, va, n):
     import oracle
-    g, its = args.grid, args.cpu_baseline_iters
+    g, its = args.grid or 200, args.cpu_baseline_iters
     b = np.ones(n)
     sample = f"same matrix (27-pt {g}^3), CG + scalar Jacobi, {its} iterations, 1 warm-up solve of 1 iteration"
     if oracle.ref() is not None:
+        oracle.ref().ref_set_num_threads(host_threads())
         oracle.ref_solve(rp, ci, va, b, np.zeros(n), precond_block=1, max_iters=1, factor=0.0, omp=True, want_hist=False)
         _, it, _, secs = oracle.ref_solve(rp, ci, va, b, np.zeros(n), precond_block=1, max_iters=its, factor=0.0,
                                           omp=True, want_hist=False)

@@ -219,9 +219,17 @@ int gkob200_dist_matrix_create(gkob200_dist_comm* comm, const gkob200_matrix* lo
                                const int32_t* gather_idxs, const int64_t* send_sizes_host,
                                const int64_t* recv_sizes_host, gkob200_dist_matrix** out);
 int gkob200_dist_matrix_destroy(gkob200_dist_matrix* m);
-/* x_local = A b  /  x_local = alpha A b + beta x_local: pack -> NCCL halo exchange on a side
- * stream overlapped with the local SpMV -> non-local SpMV
- * [ref: core/distributed/matrix.cpp:307-369] */
+/* 1 when apply() is ONE launch: the first CTAs of the local SpMV store the halo entries into
+ * the neighbours' receive windows over peer memory (NVLink) and the row blocks with non-local
+ * entries, scheduled last, wait for the neighbours' epoch flags and finish their row sums with
+ * the non-local block.  Needs: every rank on its own GPU with all peers mappable (CUDA IPC),
+ * one right-hand side, local block on the CSR row-block kernel (int32), non-local block
+ * row-compressed.  0: pack -> ncclSend/ncclRecv on a side stream overlapped with the local
+ * SpMV -> separate non-local SpMV.  GKOB200_FUSED_HALO=0 / GKOB200_P2P=0 force the latter.
+ * gkob200_dist_matrix_create is collective over the communicator either way. */
+int gkob200_dist_matrix_uses_fused_halo(const gkob200_dist_matrix* m);
+/* x_local = A b  /  x_local = alpha A b + beta x_local
+ * [ref: core/distributed/matrix.cpp:263-369 communicate + apply_impl] */
 int gkob200_dist_matrix_apply(gkob200_dist_matrix* m, void* stream, const void* b_local, int64_t b_stride,
                               int64_t nrhs, const void* alpha, const void* beta, void* x_local, int64_t x_stride);
 /* Distributed CG (kind must be GKOB200_SOLVER_CG; preconditioner none / scalar Jacobi on the

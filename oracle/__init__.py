@@ -61,6 +61,24 @@ def _c(dtype, x):
     return f64(x) if np.dtype(dtype) == np.float64 else f32(x)
 
 
+def gen_stencil_csr(kind, nx, ny, nz=1, row_begin=0, row_end=None):
+    """(row_ptrs int32, col_idxs int32, values f64, n): the BASELINE stencil matrices from the
+    oracle's own generator (independent of the product's csrc/generators.cu)."""
+    k = {"5pt": 0, "7pt": 1, "27pt": 2}[kind]
+    n = nx * ny * (1 if k == 0 else nz)
+    row_end = n if row_end is None else row_end
+    fn = lib().oracle_gen_stencil_csr
+    fn.restype = i64
+    nnz = fn(k, i64(nx), i64(ny), i64(nz), i64(row_begin), i64(row_end), None, None, None)
+    if nnz > 2 ** 31 - 1:
+        raise ValueError("int32 overflow")
+    rp = np.empty(row_end - row_begin + 1, np.int32)
+    ci = np.empty(nnz, np.int32)
+    va = np.empty(nnz, np.float64)
+    fn(k, i64(nx), i64(ny), i64(nz), i64(row_begin), i64(row_end), P(rp), P(ci), P(va))
+    return rp, ci, va, n
+
+
 # ---- plain-C oracle ---------------------------------------------------------
 def csr_spmv(rp, ci, va, b, alpha=None, beta=None, c=None):
     """c = A b, or c = alpha A b + beta c (b, c: n x k arrays)."""

@@ -113,4 +113,37 @@ void oracle_hybrid_compute_coo_row_ptrs(const uint64_t* row_nnz, int64_t n, uint
 
 #include "oracle_dist.inc"
 
-int oracle_version(void) { return 100; }
+/* Synthetic BASELINE stencils (SURVEY.md §8d "Synthetic inputs"), written independently of the
+ * product's generator (csrc/generators.cu) so that the reference arm of bench.py never loads the
+ * product library and the two generators check each other (tests/test_oracle_gen.py).
+ * kind 0: 2D 5-pt (diag 4), 1: 3D 7-pt (diag 6), 2: 3D 27-pt (diag 26); off-diagonals -1;
+ * Dirichlet truncation; rows [row_begin, row_end), GLOBAL columns ascending.
+ * Pass cols == NULL to count: returns the number of entries. */
+int64_t oracle_gen_stencil_csr(int kind, int64_t nx, int64_t ny, int64_t nz, int64_t row_begin, int64_t row_end,
+                               int32_t* row_ptrs, int32_t* cols, double* vals)
+{
+    if (kind == 0) nz = 1;
+    int64_t k = 0;
+    for (int64_t row = row_begin; row < row_end; ++row) {
+        const int64_t x = row % nx, y = (row / nx) % ny, z = row / (nx * ny);
+        if (row_ptrs) row_ptrs[row - row_begin] = (int32_t)k;
+        for (int dz = -1; dz <= 1; ++dz)
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int manhattan = abs(dx) + abs(dy) + abs(dz);
+                    if (kind != 2 && manhattan > 1) continue;
+                    if (kind == 0 && dz != 0) continue;
+                    const int64_t xx = x + dx, yy = y + dy, zz = z + dz;
+                    if (xx < 0 || xx >= nx || yy < 0 || yy >= ny || zz < 0 || zz >= nz) continue;
+                    if (cols) {
+                        cols[k] = (int32_t)((zz * ny + yy) * nx + xx);
+                        vals[k] = manhattan == 0 ? (kind == 0 ? 4.0 : kind == 1 ? 6.0 : 26.0) : -1.0;
+                    }
+                    ++k;
+                }
+    }
+    if (row_ptrs) row_ptrs[row_end - row_begin] = (int32_t)k;
+    return k;
+}
+
+int oracle_version(void) { return 101; }

@@ -198,5 +198,6 @@ def declare(lib):
         d(f"gkob200_dist_vector_build_local_{V}", [vp, i64, vp, vp, vp, i64, vp, vp, vp, i32, vp, i64])
     d("gkob200_dist_matrix_create", [vp, MP, MP, vp, vp, vp, C.POINTER(vp)])
     d("gkob200_dist_matrix_destroy", [vp])
+    d("gkob200_dist_matrix_uses_fused_halo", [vp])
     d("gkob200_dist_matrix_apply", [vp, vp, vp, i64, i64, vp, vp, vp, i64])
     d("gkob200_dist_solver_create", [C.c_int, vp, PP, SP, i64, C.POINTER(vp)])

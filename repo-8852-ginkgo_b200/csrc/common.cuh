@@ -11,6 +11,7 @@
 #include <stdint.h>
 
 #include "../../include/gko_b200.h"
+#include "p2p.cuh"
 
 namespace gkob200 {
 
@@ -218,28 +219,66 @@ __device__ __forceinline__ void store_block_partial2(T v0, T v1, T* partials)
     }
 }
 
-// grid = 1 (one reduction) or 2 (second array right behind the first, result to out2)
+// Second stage of the deferred reduction.  gridDim.x = G CTAs sum G fixed contiguous chunks of
+// the per-CTA partials (both arrays when out2 != nullptr: the second array follows the first,
+// n entries each); the CTA that draws the last ticket adds the G chunk sums in chunk order,
+// writes the result(s) and — inside a distributed solver — all-reduces `p2p_count` values at
+// `p2p_buf` over peer memory (p2p.cuh), so SpMV + dot + all-reduce are two launches.
+// Deterministic for a fixed (n, G): the association does not depend on which CTA is last.
+// (Round 1 used ONE CTA: 8 us for the 62 500 partials of a 200^3 SpMV, on the critical path of
+// every iteration.)  `chunk_sums` has room for 2 * G values, `ticket` is one zeroed word.
+constexpr int kFinishThreads = 512;
+constexpr int kFinishMaxCtas = 64;
+inline int finish_grid(int64_t n)
+{
+    int64_t g = (n + 2047) / 2048;
+    return static_cast<int>(g < 1 ? 1 : g > kFinishMaxCtas ? kFinishMaxCtas : g);
+}
+
 template <typename T>
-__global__ void __launch_bounds__(1024) finish_partials(int64_t n, const T* __restrict__ partials, T* out, const int* skip,
-                                                        T* out2 = nullptr)
+__global__ void __launch_bounds__(kFinishThreads)
+    finish_partials(int64_t n, const T* __restrict__ partials, T* out, const int* skip, T* out2, T* chunk_sums,
+                    unsigned* ticket, const P2pDev* p2p, T* p2p_buf, int p2p_count, int* on_fail)
 {
     if (skip && *skip) return;
-    if (blockIdx.x == 1) {
-        partials += n;
-        out = out2;
-    }
     __shared__ T red[32];
-    T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
-    int64_t i = threadIdx.x;
-    for (; i + 3 * 1024 < n; i += 4 * 1024) {
-        a0 += partials[i];
-        a1 += partials[i + 1024];
-        a2 += partials[i + 2048];
-        a3 += partials[i + 3072];
+    __shared__ bool is_last;
+    const int G = gridDim.x;
+    const int64_t chunk = (n + G - 1) / G;
+    const int64_t lo = blockIdx.x * chunk, hi = lo + chunk < n ? lo + chunk : n;
+    const int nv = out2 ? 2 : 1;
+    for (int a = 0; a < nv; ++a) {
+        const T* src = partials + a * n;
+        T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
+        int64_t i = lo + threadIdx.x;
+        for (; i + 3 * kFinishThreads < hi; i += 4 * kFinishThreads) {
+            a0 += src[i];
+            a1 += src[i + kFinishThreads];
+            a2 += src[i + 2 * kFinishThreads];
+            a3 += src[i + 3 * kFinishThreads];
+        }
+        for (; i < hi; i += kFinishThreads) a0 += src[i];
+        const T s = block_sum((a0 + a1) + (a2 + a3), red);
+        if (threadIdx.x == 0) chunk_sums[a * G + blockIdx.x] = s;
     }
-    for (; i < n; i += 1024) a0 += partials[i];
-    const T s = block_sum((a0 + a1) + (a2 + a3), red);
-    if (threadIdx.x == 0) out[0] = s;
+    if (G > 1) {
+        if (threadIdx.x == 0) {
+            __threadfence();
+            is_last = (atomicAdd(ticket, 1u) == static_cast<unsigned>(G) - 1u);
+        }
+        __syncthreads();
+        if (!is_last) return;
+        __threadfence();
+    }
+    if (threadIdx.x == 0) {
+        if (G > 1) *ticket = 0u;
+        for (int a = 0; a < nv; ++a) {
+            T tot = T(0);
+            for (int g = 0; g < G; ++g) tot += __ldcg(&chunk_sums[a * G + g]);
+            (a == 0 ? out : out2)[0] = tot;
+        }
+        if (p2p && !peer_allreduce(*p2p, p2p_buf, p2p_count) && on_fail) *on_fail = 1;
+    }
 }
 
 // Scratch carried by every reducing kernel: ticket words followed by partials.

@@ -118,7 +118,71 @@ __global__ void __launch_bounds__(kRowsPerCta)
 // the (at most 3) tail elements the 16-byte granularity leaves over.
 // Requires 16-byte aligned `values` / `col_idxs` base pointers.
 // ---------------------------------------------------------------------------
-template <typename V, typename I, bool Advanced, bool Fused, int kBatch>
+// ---------------------------------------------------------------------------
+// Halo exchange inside the SpMV launch (distributed matrix, p2p.cuh).  The first
+// H->n_push_ctas CTAs of the grid do not own rows: they copy the entries of b that the
+// neighbours need straight into the neighbours' receive windows (peer memory over NVLink),
+// and the last of them to finish publishes the epoch flag.  They never wait for this launch of
+// a peer — only for a peer to have ENTERED the previous epoch (flow control of the
+// double-buffered window) — so every rank's pushes complete no matter how its row CTAs are
+// scheduled.
+// ---------------------------------------------------------------------------
+template <typename V>
+__device__ __forceinline__ void halo_push_cta(const HaloDev* __restrict__ H, const V* __restrict__ b, int64_t b_stride)
+{
+    const int tid = threadIdx.x;
+    unsigned char* win = H->window;
+    const unsigned long long e = *reinterpret_cast<const unsigned long long*>(win + kHaloEpochOff);
+    __shared__ int s_fail;
+    if (tid == 0) s_fail = 0;
+    __syncthreads();
+    // (1) every neighbour learns that this rank entered epoch e (so it has finished reading
+    //     the receive buffers of all earlier epochs: those reads were earlier launches)
+    if (blockIdx.x == 0 && tid < H->n_neighbours) st_relaxed_sys(H->nb_started[tid], e);
+    // (2) flow control: buffer e&1 of a receiver still holds epoch e-2 until it entered e-1
+    if (tid < H->n_send_peers) {
+        const unsigned long long* f =
+            reinterpret_cast<const unsigned long long*>(win + kHaloStartedOff) + H->send_peer[tid];
+        if (!wait_flag_ge(f, e - 1, H->timeout_ns)) s_fail = 1;
+    }
+    __syncthreads();
+    if (s_fail) {
+        // never publish `arrived`: the receivers time out as well and every rank reports the error
+        if (tid == 0) *reinterpret_cast<volatile int*>(win + kHaloErrorOff) = 1;
+        return;
+    }
+    // (3) this CTA's share of the send list
+    const int n_push = H->n_push_ctas;
+    const long long total = H->send_total;
+    long long per = (total + n_push - 1) / n_push;
+    per = (per + kRowsPerCta - 1) / kRowsPerCta * kRowsPerCta;
+    const long long begin = per * blockIdx.x;
+    const long long end = begin + per < total ? begin + per : total;
+    const int nsp = H->n_send_peers;
+    const size_t parity_off = static_cast<size_t>(e & 1);
+#pragma unroll 4
+    for (long long t = begin + tid; t < end; t += kRowsPerCta) {
+        int i = 0;
+        while (i + 1 < nsp && t >= H->send_begin[i + 1]) ++i;
+        const V v = b[static_cast<int64_t>(H->gather[t]) * b_stride];
+        V* dst = reinterpret_cast<V*>(H->dst_data[i] + parity_off * static_cast<size_t>(H->dst_stride[i])) +
+                 (t - H->send_begin[i]);
+        *dst = v;
+    }
+    // (4) all entries of all push CTAs before the flags
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        unsigned* ticket = reinterpret_cast<unsigned*>(win + kHaloTicketOff);
+        if (atomicAdd(ticket, 1u) == static_cast<unsigned>(n_push) - 1u) {
+            *ticket = 0u;
+            __threadfence_system();
+            for (int i = 0; i < nsp; ++i) st_relaxed_sys(H->dst_arrived[i], e);
+        }
+    }
+}
+
+template <typename V, typename I, bool Advanced, bool Fused, int kBatch, bool Halo = false>
 __global__ void __launch_bounds__(kRowsPerCta)
     csr_spmv_rowblock_tma(int64_t n_rows, const I* __restrict__ row_ptrs, const I* __restrict__ col_idxs,
                           const V* __restrict__ values, const V* __restrict__ b, int64_t b_stride,
@@ -134,7 +198,27 @@ __global__ void __launch_bounds__(kRowsPerCta)
     __shared__ __align__(8) uint64_t bar;
 
     const int tid = threadIdx.x;
-    const int64_t row0 = static_cast<int64_t>(blockIdx.x) * kRowsPerCta;
+    int64_t blk = blockIdx.x;
+    int nl_slot = -1;   // >= 0: this CTA owns rows with non-local entries (index into nl_slot_begin)
+    if (Halo) {
+        const HaloDev* __restrict__ H = fu.halo;
+        if (fu.skip && *fu.skip) return;   // uniform (push CTAs included: no rank pushes after the stop)
+        const int n_push = H->n_push_ctas;
+        if (static_cast<int>(blockIdx.x) < n_push) {
+            halo_push_cta<V>(H, b, b_stride);
+            if (Fused && fu.out && tid == 0) {   // the deferred reduction reads one partial per CTA
+                ws_partials<V>(fu.ws)[blockIdx.x] = V(0);
+                if (fu.out_sq) ws_partials<V>(fu.ws)[gridDim.x + blockIdx.x] = V(0);
+            }
+            return;
+        }
+        // interior row blocks first, blocks with non-local rows last: by the time they run the
+        // neighbours' entries have normally arrived and nobody spins
+        const int slot = static_cast<int>(blockIdx.x) - n_push;
+        blk = H->order[slot];
+        if (slot >= H->n_interior) nl_slot = slot - H->n_interior;
+    }
+    const int64_t row0 = blk * kRowsPerCta;
     const int nrow = static_cast<int>(min(static_cast<int64_t>(kRowsPerCta), n_rows - row0));
     if (tid == 0) mbar_init(&bar, 1);
     // Independent loads issued back to back so that their latencies overlap: the solver's
@@ -213,6 +297,43 @@ __global__ void __launch_bounds__(kRowsPerCta)
                 if (k + u < hi)
                     acc = Advanced ? add_rn(acc, mul_rn(mul_rn(alpha, v[u]), xv[u]))
                                    : add_rn(acc, mul_rn(v[u], xv[u]));
+            }
+        }
+    }
+    if (Halo && nl_slot >= 0) {
+        // Non-local entries of this block's rows: c = 1*c + A_nl * ghost continues the row sums
+        // in storage order (reference: non_local_mtx_->apply(one, recv, one, x) after the local
+        // apply, core/distributed/matrix.cpp:312-333; advanced apply: alpha in front) — the
+        // result is bit-identical to two separate applies.
+        const HaloDev* __restrict__ H = fu.halo;
+        unsigned char* win = H->window;
+        __shared__ int s_wait_ok;
+        __syncthreads();   // everyone is done with the staged tile: its space becomes the row map
+        int* s_nl = reinterpret_cast<int*>(smem_raw);
+        s_nl[tid] = -1;
+        if (tid == 0) s_wait_ok = 1;
+        __syncthreads();
+        const unsigned long long e = *reinterpret_cast<const unsigned long long*>(win + kHaloEpochOff);
+        if (tid < H->n_recv_peers) {
+            const unsigned long long* f =
+                reinterpret_cast<const unsigned long long*>(win + kHaloArrivedOff) + H->recv_peer[tid];
+            if (!wait_flag_ge(f, e, H->timeout_ns)) {
+                s_wait_ok = 0;
+                *reinterpret_cast<volatile int*>(win + kHaloErrorOff) = 1;
+            }
+        }
+        const int j0 = H->nl_slot_begin[nl_slot], j1 = H->nl_slot_begin[nl_slot + 1];
+        for (int j = j0 + tid; j < j1; j += kRowsPerCta) s_nl[H->nl_row_list[j] - row0] = j;
+        __syncthreads();
+        const int j = s_nl[tid];
+        if (j >= 0 && s_wait_ok) {
+            // (L2 loads: the window is written by the peers, never through this SM's L1)
+            const V* recv = reinterpret_cast<const V*>(win + kHaloDataOff) + (e & 1) * H->recv_stride;
+            const V* nl_vals = static_cast<const V*>(H->nl_vals);
+            const int k1 = H->nl_row_ptrs[j + 1];
+            for (int k = H->nl_row_ptrs[j]; k < k1; ++k) {
+                const V v = Advanced ? mul_rn(alpha, nl_vals[k]) : nl_vals[k];
+                acc = add_rn(acc, mul_rn(v, __ldcg(recv + H->nl_cols[k])));
             }
         }
     }
@@ -560,10 +681,18 @@ int csr_spmv_launch(cudaStream_t s, int64_t n_rows, int64_t n_cols, int64_t nnz,
         const int cap = rowblock_cap(max_block_nnz, sizeof(V) + sizeof(I));
         const size_t smem = align16(static_cast<size_t>(padded_size(cap)) * sizeof(V)) +
                             align16(static_cast<size_t>(padded_size(cap)) * sizeof(I)) + 64;
-        const unsigned grid = static_cast<unsigned>(ceildiv(n_rows, kRowsPerCta));
+        const bool halo = fused && fu.halo != nullptr;
+        const unsigned grid = static_cast<unsigned>(ceildiv(n_rows, kRowsPerCta)) + (halo ? fu.halo_push_ctas : 0);
         const bool aligned = (reinterpret_cast<uintptr_t>(values) % 16 == 0) &&
                              (reinterpret_cast<uintptr_t>(col_idxs) % 16 == 0);
+        // the halo exchange only exists in the bulk-async kernel with 32-bit indices
+        if (halo && !(aligned && rowblock_variant() == 1 && sizeof(I) == 4)) return GKOB200_EUNSUPPORTED;
         if (aligned && rowblock_variant() == 1) {
+            // the deferred reduction leaves one partial per CTA (and array) in fu.ws
+            if (fused && fu.out &&
+                static_cast<int64_t>(grid) * (fu.out_sq ? 2 : 1) + 2 * kFinishMaxCtas >
+                    (fu.ws_blocks + 256) * kReduceMaxVals)
+                return GKOB200_EWORKSPACE;
             // stream-ahead distance: one wave of resident CTAs (shared-memory or thread bound)
             int resident = static_cast<int>((227 * 1024) / (smem + 1024));
             if (resident > 16) resident = 16;
@@ -576,14 +705,20 @@ int csr_spmv_launch(cudaStream_t s, int64_t n_rows, int64_t n_cols, int64_t nnz,
                 const double mean = static_cast<double>(nnz) / static_cast<double>(n_rows);
                 batch = mean <= 5.5 ? 5 : mean <= 7.5 ? 7 : mean <= 10.5 ? 9 : 14;
             }
-#define GKOB200_RBT(ADV, FUSED, BATCH)                                                                \
-    csr_spmv_rowblock_tma<V, I, ADV, FUSED, BATCH><<<grid, kRowsPerCta, smem, s>>>(                   \
+#define GKOB200_RBT(ADV, FUSED, BATCH, HALO)                                                          \
+    csr_spmv_rowblock_tma<V, I, ADV, FUSED, BATCH, HALO><<<grid, kRowsPerCta, smem, s>>>(             \
         n_rows, row_ptrs, col_idxs, values, b, b_stride, alpha, beta, c, c_stride, cap, fu, pf, nnz)
-#define GKOB200_RBT_B(BATCH)                                  \
-    if (adv && fused) GKOB200_RBT(true, true, BATCH);         \
-    else if (adv) GKOB200_RBT(true, false, BATCH);            \
-    else if (fused) GKOB200_RBT(false, true, BATCH);          \
-    else GKOB200_RBT(false, false, BATCH)
+#define GKOB200_RBT_B(BATCH)                                                        \
+    if (halo) {                                                                     \
+        if constexpr (sizeof(I) == 4) {                                             \
+            if (adv) GKOB200_RBT(true, true, BATCH, true);                          \
+            else GKOB200_RBT(false, true, BATCH, true);                             \
+        }                                                                           \
+    }                                                                               \
+    else if (adv && fused) GKOB200_RBT(true, true, BATCH, false);                   \
+    else if (adv) GKOB200_RBT(true, false, BATCH, false);                           \
+    else if (fused) GKOB200_RBT(false, true, BATCH, false);                         \
+    else GKOB200_RBT(false, false, BATCH, false)
             if (batch >= 14) { GKOB200_RBT_B(14); }
             else if (batch >= 9) { GKOB200_RBT_B(9); }
             else if (batch >= 7) { GKOB200_RBT_B(7); }
@@ -591,11 +726,7 @@ int csr_spmv_launch(cudaStream_t s, int64_t n_rows, int64_t n_cols, int64_t nnz,
 #undef GKOB200_RBT_B
 #undef GKOB200_RBT
             GKOB200_CHECK_LAUNCH();
-            if (fused && fu.out) {
-                finish_partials<V><<<fu.out_sq ? 2 : 1, 1024, 0, s>>>(static_cast<int64_t>(grid), ws_partials<V>(fu.ws),
-                                                                      fu.out, fu.skip, fu.out_sq);
-                GKOB200_CHECK_LAUNCH();
-            }
+            if (fused && fu.out) return launch_finish_partials<V>(s, static_cast<int64_t>(grid), fu);
             return 0;
         }
         if (fused && fu.out && static_cast<int64_t>(grid) * (fu.out_sq ? 2 : 1) > fu.ws_blocks) return GKOB200_EWORKSPACE;

@@ -5,16 +5,26 @@
 // (reference core/distributed/matrix.cpp:263-369) and the all_reduce steps of
 // experimental::distributed::Vector (core/distributed/vector.cpp:317-407).  The reference
 // packs with row_gather, calls exec->synchronize() (a device-wide sync), stages through
-// HOST buffers unless MPI is GPU-aware and posts MPI_Ialltoallv; here
+// HOST buffers unless MPI is GPU-aware, posts MPI_Ialltoallv and launches a second SpMV.
+//
+// Fused path (every rank on its own GPU, peers mappable, one right-hand side, local block on
+// the CSR row-block kernel): ONE launch per apply.  The first CTAs of the SpMV grid store the
+// entries the neighbours need straight into the neighbours' receive windows over peer memory
+// and publish an epoch flag; the row blocks that own non-local entries are scheduled last,
+// wait for the neighbours' flags and continue their row sums with the non-local entries
+// (csr_spmv.cu, p2p.cuh).  No pack kernel, no NCCL call, no second launch, no events; the
+// distributed CG iteration is four launches, captured in a CUDA graph.
+//
+// Fallback path (GKOB200_P2P=0, ranks sharing a GPU, many right-hand sides, other formats):
 //   * the pack kernel runs on the compute stream, an event hands the send buffer to a
-//     dedicated communication stream, the halo moves GPU->GPU as grouped ncclSend/ncclRecv
-//     (NVLink 5 through NVSwitch, device buffers only),
+//     dedicated communication stream, the halo moves GPU->GPU as grouped ncclSend/ncclRecv,
 //   * the local SpMV overlaps the exchange on the compute stream,
 //   * a second event gates the non-local SpMV  x += A_nl * ghost,
-//   * dot products are reduced with ncclAllReduce on 1-2 scalars that never visit the host.
-// No device-wide synchronisation anywhere on the path.
+//   * dot products are reduced with ncclAllReduce (or the peer-memory all-reduce).
+// No device-wide synchronisation anywhere on either path.
 #include <nccl.h>
 
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -27,6 +37,7 @@
         if (r__ != ncclSuccess) return 1000 + static_cast<int>(r__); \
     } while (0)
 
+using gkob200::HaloDev;
 using gkob200::P2pDev;
 using gkob200::kP2pMaxRanks;
 using gkob200::kP2pBlockBytes;
@@ -37,6 +48,7 @@ struct gkob200_dist_comm {
     int rank = 0, size = 1;
     cudaStream_t comm_stream = nullptr;
     bool p2p = false;
+    unsigned long long timeout_ns = 30ull * 1000 * 1000 * 1000;
     P2pDev p2p_dev{};
     P2pDev* p2p_dev_ptr = nullptr;   // device copy (for kernels that get it through a pointer)
 };
@@ -51,7 +63,13 @@ struct gkob200_dist_matrix {
     int64_t buf_nrhs = 0;
     cudaEvent_t packed = nullptr, received = nullptr;
     int64_t launches = 0;
-    bool exchanged = false;   // the last apply all-reduced its fused dot inside the non-local kernel
+    bool exchanged = false;   // the last apply all-reduced its fused dot itself
+    // ---- fused halo (peer-memory window) ----
+    bool fused = false;
+    unsigned char* window = nullptr;                  // local window (cudaMalloc)
+    unsigned char* peer_window[kP2pMaxRanks] = {};    // IPC mappings (peer_window[rank] == window)
+    gkob200::DevBuf halo_dev, order, nl_slot_begin;
+    int n_push = 0;
 };
 
 namespace gkob200 {
@@ -66,36 +84,51 @@ ncclDataType_t nccl_type<float>() { return ncclFloat; }
 
 // stand-alone all-reduce (ranks whose producing kernel cannot do the exchange itself)
 template <typename V>
-__global__ void p2p_allreduce_kernel(P2pDev pr, V* buf, int count, const int* skip)
+__global__ void p2p_allreduce_kernel(P2pDev pr, V* buf, int count, const int* skip, int* on_fail)
 {
     // `skip`: the solver's stopped flag — identical on every rank (it derives from all-reduced
     // values), and the fused exchanges inside the solver kernels honour it too
     if (skip && *skip) return;
-    peer_allreduce(pr, buf, count);
+    if (!peer_allreduce(pr, buf, count) && on_fail) *on_fail = 1;
 }
 
-// Exchanges IPC handles + device UUIDs through the NCCL communicator and maps the peers'
-// blocks.  Used only if EVERY rank could map every peer and all ranks sit on distinct GPUs
-// (two spinning ranks time-slicing one GPU would wait for each other).
-int p2p_setup(gkob200_dist_comm* c)
+// the kernel in front of a fused-halo SpMV enters the next epoch (p2p.cuh)
+__global__ void halo_epoch_bump(unsigned char* window, const int* skip)
 {
-    const char* env = getenv("GKOB200_P2P");
-    if ((env && env[0] == '0') || c->size > kP2pMaxRanks) return 0;
+    if (skip && *skip) return;
+    ++*reinterpret_cast<unsigned long long*>(window + kHaloEpochOff);
+}
+
+// Collective over the communicator: every rank allocates `bytes` of zeroed device memory and
+// maps the allocations of all the others (CUDA IPC).  Each rank contributes `extra` (<= 160
+// bytes) that every rank receives in `extras` (size * 160 bytes).  *ok = 1 only if EVERY rank
+// could map every peer, all ranks sit on distinct GPUs (two spinning ranks time-slicing one GPU
+// would wait for each other) and every rank passed want != 0; otherwise nothing stays mapped.
+constexpr size_t kExtraBytes = 160;
+int p2p_shared_alloc(gkob200_dist_comm* c, size_t bytes, int want, const void* extra, size_t extra_bytes,
+                     unsigned char** ptrs, std::vector<unsigned char>* extras, int* ok_out)
+{
     struct Record {
         cudaIpcMemHandle_t handle;
         char uuid[16];
-        char pad[128 - sizeof(cudaIpcMemHandle_t) - 16];
+        int want;
+        char pad[12];
+        unsigned char extra[kExtraBytes];
     };
-    static_assert(sizeof(Record) == 128, "record size");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64 && sizeof(Record) == 256, "record size");
+    *ok_out = 0;
+    if (extra_bytes > kExtraBytes) return GKOB200_EINVAL;
     unsigned char* local = nullptr;
-    GKOB200_CUDA(cudaMalloc(&local, kP2pBlockBytes));
-    GKOB200_CUDA(cudaMemset(local, 0, kP2pBlockBytes));
+    GKOB200_CUDA(cudaMalloc(&local, bytes));
+    GKOB200_CUDA(cudaMemset(local, 0, bytes));
     Record mine{};
     int dev = 0;
     GKOB200_CUDA(cudaGetDevice(&dev));
     cudaDeviceProp prop;
     GKOB200_CUDA(cudaGetDeviceProperties(&prop, dev));
     memcpy(mine.uuid, &prop.uuid, 16);
+    mine.want = want;
+    if (extra && extra_bytes) memcpy(mine.extra, extra, extra_bytes);
     int ok = cudaIpcGetMemHandle(&mine.handle, local) == cudaSuccess ? 1 : 0;
     cudaGetLastError();
     unsigned char* d_rec = nullptr;
@@ -105,20 +138,22 @@ int p2p_setup(gkob200_dist_comm* c)
     GKOB200_CUDA(cudaStreamSynchronize(c->comm_stream));
     std::vector<Record> all(c->size);
     GKOB200_CUDA(cudaMemcpy(all.data(), d_rec + sizeof(Record), sizeof(Record) * c->size, cudaMemcpyDeviceToHost));
-    c->p2p_dev.rank = c->rank;
-    c->p2p_dev.size = c->size;
-    for (int r = 0; r < c->size && ok; ++r) {
+    for (int r = 0; r < c->size; ++r) ptrs[r] = nullptr;
+    for (int r = 0; r < c->size; ++r) {
+        if (!all[r].want) ok = 0;
         for (int q = 0; q < r; ++q)
             if (memcmp(all[r].uuid, all[q].uuid, 16) == 0) ok = 0;   // two ranks on one GPU
+    }
+    for (int r = 0; r < c->size; ++r) {
         if (r == c->rank) {
-            c->p2p_dev.block[r] = local;
+            ptrs[r] = local;
         } else if (ok) {
             void* ptr = nullptr;
             if (cudaIpcOpenMemHandle(&ptr, all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
                 cudaGetLastError();
                 ok = 0;
             }
-            c->p2p_dev.block[r] = static_cast<unsigned char*>(ptr);
+            ptrs[r] = static_cast<unsigned char*>(ptr);
         }
     }
     // all or nobody
@@ -128,32 +163,201 @@ int p2p_setup(gkob200_dist_comm* c)
     GKOB200_CUDA(cudaStreamSynchronize(c->comm_stream));
     GKOB200_CUDA(cudaMemcpy(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost));
     cudaFree(d_rec);
-    c->p2p = ok != 0;
-    if (c->p2p) {
-        GKOB200_CUDA(cudaMalloc(&c->p2p_dev_ptr, sizeof(P2pDev)));
-        GKOB200_CUDA(cudaMemcpy(c->p2p_dev_ptr, &c->p2p_dev, sizeof(P2pDev), cudaMemcpyHostToDevice));
+    if (extras) {
+        extras->resize(static_cast<size_t>(c->size) * kExtraBytes);
+        for (int r = 0; r < c->size; ++r) memcpy(extras->data() + r * kExtraBytes, all[r].extra, kExtraBytes);
     }
-    if (!c->p2p) {
-        for (int r = 0; r < c->size; ++r)
-            if (r != c->rank && c->p2p_dev.block[r]) cudaIpcCloseMemHandle(c->p2p_dev.block[r]);
+    if (!ok) {
+        for (int r = 0; r < c->size; ++r) {
+            if (r != c->rank && ptrs[r]) cudaIpcCloseMemHandle(ptrs[r]);
+            ptrs[r] = nullptr;
+        }
         cudaGetLastError();
         cudaFree(local);
-        c->p2p_dev = P2pDev{};
+    }
+    *ok_out = ok;
+    return 0;
+}
+
+void p2p_shared_free(gkob200_dist_comm* c, unsigned char** ptrs)
+{
+    for (int r = 0; r < c->size; ++r) {
+        if (!ptrs[r]) continue;
+        if (r == c->rank)
+            cudaFree(ptrs[r]);
+        else
+            cudaIpcCloseMemHandle(ptrs[r]);
+        ptrs[r] = nullptr;
+    }
+    cudaGetLastError();
+}
+
+// Maps one 4 KB scalar block per rank (p2p.cuh) for the in-kernel all-reduces.
+int p2p_setup(gkob200_dist_comm* c)
+{
+    const char* env = getenv("GKOB200_P2P");
+    if (const char* t = getenv("GKOB200_P2P_TIMEOUT_MS")) {
+        const long long ms = atoll(t);
+        if (ms > 0) c->timeout_ns = static_cast<unsigned long long>(ms) * 1000000ull;
+    }
+    const int want = !((env && env[0] == '0') || c->size > kP2pMaxRanks);
+    int ok = 0;
+    unsigned char* ptrs[kP2pMaxRanks] = {};
+    if (c->size > kP2pMaxRanks) return 0;   // (cannot even take part in the exchange)
+    int rc = p2p_shared_alloc(c, kP2pBlockBytes, want, nullptr, 0, ptrs, nullptr, &ok);
+    if (rc) return rc;
+    c->p2p = ok != 0;
+    if (c->p2p) {
+        c->p2p_dev.rank = c->rank;
+        c->p2p_dev.size = c->size;
+        c->p2p_dev.timeout_ns = c->timeout_ns;
+        for (int r = 0; r < c->size; ++r) c->p2p_dev.block[r] = ptrs[r];
+        GKOB200_CUDA(cudaMalloc(&c->p2p_dev_ptr, sizeof(P2pDev)));
+        GKOB200_CUDA(cudaMemcpy(c->p2p_dev_ptr, &c->p2p_dev, sizeof(P2pDev), cudaMemcpyHostToDevice));
     }
     return 0;
 }
 
 // in-place sum of `count` scalars over all ranks, on stream s
 template <typename V>
-int comm_allreduce(gkob200_dist_comm* c, cudaStream_t s, V* buf, size_t count, const int* skip = nullptr)
+int comm_allreduce(gkob200_dist_comm* c, cudaStream_t s, V* buf, size_t count, const int* skip = nullptr,
+                   int* on_fail = nullptr)
 {
     if (!c || c->size == 1 || count == 0) return 0;
     if (c->p2p && count <= 4) {
-        p2p_allreduce_kernel<V><<<1, 1, 0, s>>>(c->p2p_dev, buf, static_cast<int>(count), skip);
+        p2p_allreduce_kernel<V><<<1, 1, 0, s>>>(c->p2p_dev, buf, static_cast<int>(count), skip, on_fail);
         GKOB200_CHECK_LAUNCH();
         return 0;
     }
     GKOB200_NCCL(ncclAllReduce(buf, buf, count, nccl_type<V>(), ncclSum, c->comm, s));
+    return 0;
+}
+
+// ---- fused halo: plan ------------------------------------------------------------------
+// true when matrix_apply runs this descriptor on the bulk-async CSR row-block kernel with
+// 32-bit indices (the only kernel that carries the halo exchange)
+bool local_block_takes_halo(const gkob200_matrix& A)
+{
+    if (A.format != GKOB200_FMT_CSR || A.index_type != GKOB200_I32) return false;
+    int strategy = A.csr_strategy;
+    if (strategy == GKOB200_CSR_AUTO)
+        strategy = A.csr_max_block_nnz > 0 ? gkob200_csr_pick_strategy(A.n_rows, A.nnz, -1, A.csr_max_block_nnz)
+                                           : GKOB200_CSR_MERGE_PATH;
+    if (strategy != GKOB200_CSR_CLASSICAL) return false;
+    if (reinterpret_cast<uintptr_t>(A.values) % 16 || reinterpret_cast<uintptr_t>(A.col_idxs) % 16) return false;
+    if (const char* e = getenv("GKOB200_CSR_ROWBLOCK"))
+        if (e[0] == 'p') return false;
+    return A.n_rows > 0;
+}
+
+// Collective (called by every rank from gkob200_dist_matrix_create).  Allocates and maps the
+// receive windows, exchanges the offsets at which every rank's entries land in its peers'
+// buffers, builds the CTA order (row blocks with non-local rows last) and uploads the plan.
+int halo_setup(gkob200_dist_matrix* m)
+{
+    gkob200_dist_comm* c = m->comm;
+    if (!c || c->size == 1 || !c->p2p) return 0;
+    const char* env = getenv("GKOB200_FUSED_HALO");
+    const size_t vbytes = m->local.value_type == GKOB200_F64 ? 8 : 4;
+    const bool nl_ok = m->non_local.nnz == 0 ||
+                       (m->non_local.format == GKOB200_FMT_CSR_ROWS && m->non_local.index_type == GKOB200_I32 &&
+                        m->non_local.value_type == m->local.value_type);
+    const int want = !(env && env[0] == '0') && local_block_takes_halo(m->local) && nl_ok &&
+                     m->recv_total < (int64_t(1) << 31) && m->send_total < (int64_t(1) << 31);
+    const int64_t recv_stride = (m->recv_total + 31) / 32 * 32 + 32;
+    struct Extra {
+        int64_t recv_offsets[kP2pMaxRanks];
+        int64_t recv_stride;
+        int64_t value_bytes;
+    } mine{};
+    static_assert(sizeof(Extra) <= kExtraBytes, "extra");
+    for (int p = 0; p < c->size; ++p) mine.recv_offsets[p] = m->recv_offsets[p];
+    mine.recv_stride = recv_stride;
+    mine.value_bytes = static_cast<int64_t>(vbytes);
+    std::vector<unsigned char> extras;
+    int ok = 0;
+    const size_t win_bytes = kHaloDataOff + 2 * static_cast<size_t>(recv_stride) * vbytes;
+    int rc = p2p_shared_alloc(c, win_bytes, want, &mine, sizeof(mine), m->peer_window, &extras, &ok);
+    if (rc) return rc;
+    if (!ok) return 0;
+    m->window = m->peer_window[c->rank];
+    auto extra_of = [&](int r) { return reinterpret_cast<const Extra*>(extras.data() + r * kExtraBytes); };
+
+    HaloDev H{};
+    H.rank = c->rank;
+    H.size = c->size;
+    H.timeout_ns = c->timeout_ns;
+    H.window = m->window;
+    H.send_total = m->send_total;
+    H.gather = m->gather_idxs;
+    H.recv_stride = recv_stride;
+    bool neighbour[kP2pMaxRanks] = {};
+    for (int p = 0; p < c->size; ++p) {
+        if (p == c->rank) continue;
+        if (m->send_sizes[p] > 0) {
+            const int i = H.n_send_peers++;
+            H.send_peer[i] = p;
+            H.send_begin[i] = m->send_offsets[p];
+            H.send_begin[i + 1] = m->send_offsets[p + 1];
+            const Extra* ex = extra_of(p);
+            H.dst_data[i] = m->peer_window[p] + kHaloDataOff + static_cast<size_t>(ex->recv_offsets[c->rank]) * vbytes;
+            H.dst_stride[i] = ex->recv_stride * static_cast<int64_t>(vbytes);
+            H.dst_arrived[i] = reinterpret_cast<unsigned long long*>(m->peer_window[p] + kHaloArrivedOff) + c->rank;
+            neighbour[p] = true;
+        }
+        if (m->recv_sizes[p] > 0) {
+            H.recv_peer[H.n_recv_peers++] = p;
+            neighbour[p] = true;
+        }
+    }
+    for (int p = 0; p < c->size; ++p)
+        if (neighbour[p])
+            H.nb_started[H.n_neighbours++] =
+                reinterpret_cast<unsigned long long*>(m->peer_window[p] + kHaloStartedOff) + c->rank;
+    // (send lists are grouped by peer in rank order: send_begin[i+1] == the next peer's begin,
+    //  peers without entries are skipped — their ranges are empty)
+    m->n_push = H.n_neighbours == 0 ? 0
+                                    : static_cast<int>(std::min<int64_t>(
+                                          sm_count(), std::max<int64_t>(1, ceildiv(m->send_total, 4096))));
+    H.n_push_ctas = m->n_push;
+
+    // CTA order: row blocks (128 rows) without non-local rows first, the others last
+    const int64_t n_blocks = ceildiv(m->local.n_rows, 128);
+    std::vector<int32_t> row_list(static_cast<size_t>(m->non_local.nnz > 0 ? m->non_local.n_listed : 0));
+    if (!row_list.empty())
+        GKOB200_CUDA(cudaMemcpy(row_list.data(), m->non_local.row_list, row_list.size() * sizeof(int32_t),
+                                cudaMemcpyDeviceToHost));
+    std::vector<int32_t> order, slot_begin, boundary;
+    std::vector<char> is_boundary(static_cast<size_t>(n_blocks), 0);
+    for (size_t j = 0; j < row_list.size(); ++j) {
+        const int32_t blk = row_list[j] / 128;
+        if (blk < 0 || blk >= n_blocks || (j > 0 && row_list[j] <= row_list[j - 1])) return GKOB200_EINVAL;
+        if (boundary.empty() || boundary.back() != blk) {
+            boundary.push_back(blk);
+            slot_begin.push_back(static_cast<int32_t>(j));
+            is_boundary[blk] = 1;
+        }
+    }
+    slot_begin.push_back(static_cast<int32_t>(row_list.size()));
+    order.reserve(static_cast<size_t>(n_blocks));
+    for (int64_t b = 0; b < n_blocks; ++b)
+        if (!is_boundary[b]) order.push_back(static_cast<int32_t>(b));
+    H.n_interior = static_cast<int>(order.size());
+    order.insert(order.end(), boundary.begin(), boundary.end());
+    if ((rc = m->order.alloc(order.size() * sizeof(int32_t) + 16))) return rc;
+    if ((rc = m->nl_slot_begin.alloc(slot_begin.size() * sizeof(int32_t) + 16))) return rc;
+    GKOB200_CUDA(cudaMemcpy(m->order.p, order.data(), order.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    GKOB200_CUDA(cudaMemcpy(m->nl_slot_begin.p, slot_begin.data(), slot_begin.size() * sizeof(int32_t),
+                            cudaMemcpyHostToDevice));
+    H.order = m->order.as<int32_t>();
+    H.nl_slot_begin = m->nl_slot_begin.as<int32_t>();
+    H.nl_row_list = m->non_local.row_list;
+    H.nl_row_ptrs = static_cast<const int32_t*>(m->non_local.row_ptrs);
+    H.nl_cols = static_cast<const int32_t*>(m->non_local.col_idxs);
+    H.nl_vals = m->non_local.values;
+    if ((rc = m->halo_dev.alloc(sizeof(HaloDev)))) return rc;
+    GKOB200_CUDA(cudaMemcpy(m->halo_dev.p, &H, sizeof(HaloDev), cudaMemcpyHostToDevice));
+    m->fused = true;
     return 0;
 }
 
@@ -188,14 +392,31 @@ int ensure_buffers(gkob200_dist_matrix* m, int64_t nrhs)
 }
 
 // x = A b  or  x = alpha A b + beta x  on the local rows.  `fusion` (nrhs == 1): skip flag
-// and the dot w.(A b) are attached to the LAST SpMV of the sequence.
+// and the dot w.(A b) are attached to the LAST SpMV of the sequence.  `epoch_bumped`: the
+// caller's previous kernel already entered the next halo epoch (distributed CG).
 template <typename V>
 int dist_apply(gkob200_dist_matrix* m, cudaStream_t s, const V* b, int64_t bs, int64_t nrhs, const V* alpha,
-               const V* beta, V* x, int64_t xs, const SpmvFusion<V>* fusion)
+               const V* beta, V* x, int64_t xs, const SpmvFusion<V>* fusion, bool epoch_bumped = false)
 {
     int rc;
-    if ((rc = ensure_buffers<V>(m, nrhs))) return rc;
     gkob200_dist_comm* c = m->comm;
+    if (m->fused && nrhs == 1) {
+        // ---- fused path: one launch (+ the deferred-reduction finish when a dot is attached)
+        SpmvFusion<V> fu;
+        if (fusion) fu = *fusion;
+        if (!epoch_bumped) {
+            halo_epoch_bump<<<1, 1, 0, s>>>(m->window, fu.skip);
+            GKOB200_CHECK_LAUNCH();
+            ++m->launches;
+        }
+        fu.halo = m->halo_dev.as<HaloDev>();
+        fu.halo_push_ctas = m->n_push;
+        m->exchanged = fu.out != nullptr && fu.p2p != nullptr;
+        if ((rc = matrix_apply<V>(s, m->local, b, bs, 1, alpha, beta, x, xs, &fu))) return rc;
+        m->launches += fu.out ? 2 : 1;
+        return 0;
+    }
+    if ((rc = ensure_buffers<V>(m, nrhs))) return rc;
     const bool has_halo = (m->send_total > 0 || m->recv_total > 0) && c && c->size > 1;
     V* send = m->send_buf.as<V>();
     V* recv = m->recv_buf.as<V>();
@@ -228,7 +449,7 @@ int dist_apply(gkob200_dist_matrix* m, cudaStream_t s, const V* b, int64_t bs, i
     // With a row-compressed non-local block the dot w.(A b) is split: the local SpMV
     // reduces w.(A_loc b) into out[0], the non-local kernel its own contribution into out[1]
     // (the caller adds the two after the all-reduce).  With a full-height non-local CSR the
-    // dot is taken once, by the non-local SpMV, on the final result.
+    // dot is taken once, by the non-local SpMV, on the final result, and out[1] is zeroed.
     const bool split = nl && m->non_local.format == GKOB200_FMT_CSR_ROWS;
     SpmvFusion<V> fl, fn;
     if (fusion) {
@@ -241,6 +462,9 @@ int dist_apply(gkob200_dist_matrix* m, cudaStream_t s, const V* b, int64_t bs, i
         if (split && fn.out) fn.out = fn.out + 1;
         fl.p2p = nullptr;   // only the last kernel of the apply may exchange
         if (!(split && fn.out)) fn.p2p = nullptr;
+        // out[1] is only written by the row-compressed non-local kernel: every other case must
+        // not hand the previous iteration's (all-reduced) value to the caller's sum again
+        if (fusion->out && nrhs == 1 && !split) GKOB200_CUDA(cudaMemsetAsync(fusion->out + 1, 0, sizeof(V), s));
     }
     m->exchanged = fusion && nl && fn.p2p != nullptr;
     if ((rc = matrix_apply<V>(s, m->local, b, bs, nrhs, alpha, beta, x, xs, fusion ? &fl : nullptr))) return rc;
@@ -253,13 +477,18 @@ int dist_apply(gkob200_dist_matrix* m, cudaStream_t s, const V* b, int64_t bs, i
                                   fusion ? &fn : nullptr)))
             return rc;
         ++m->launches;
-    } else if (fusion && fusion->out && nrhs == 1) {
-        GKOB200_CUDA(cudaMemsetAsync(fusion->out + 1, 0, sizeof(V), s));
     }
     return 0;
 }
 
 // ------------------------------- distributed CG --------------------------------
+// Reference loop: core/solver/cg.cpp:157-193 on distributed::Vector / distributed::Matrix.
+// Fused path, per iteration (graph-captured, `chunk` iterations per graph):
+//   dist_cg_direction   p = z + (rho/prev_rho) p ; enters the next halo epoch
+//   SpMV                q = A p : halo push + local rows + non-local rows + per-CTA partials of p.q
+//   finish_partials     p.q summed, all-reduced over peer memory
+//   dist_cg_update      x += t p, r -= t q, z = D^-1 r, (r.z, r.r) reduced, all-reduced over peer
+//                       memory, rho bookkeeping, stopping criterion
 enum { D_RHO = 0, D_PREV_RHO, D_BETA, D_BETA2, D_TAU, D_ORIG_TAU, D_RED0, D_RED1, D_COUNT };
 
 template <typename V>
@@ -275,6 +504,7 @@ struct DistCgParams {
     int64_t max_iters;
     void* ws;
     const P2pDev* p2p;   // non-null: the reduction finaliser all-reduces over peer memory itself
+    unsigned long long* halo_epoch;   // non-null: dist_cg_direction enters the next halo epoch
 };
 
 // x += t p ; r -= t q ; z = M^-1 r ; partial sums (r.z, r.r) -> sc[D_RED0..1]
@@ -313,7 +543,10 @@ __global__ void __launch_bounds__(256) dist_cg_update(DistCgParams<V> P)
         if (Q.p2p) {
             // all-reduce over peer memory + rho bookkeeping + criterion, all in this finaliser
             // (otherwise: ncclAllReduce + dist_cg_scalars, two more launches)
-            peer_allreduce(*Q.p2p, Q.sc + D_RED0, 2);
+            if (!peer_allreduce(*Q.p2p, Q.sc + D_RED0, 2)) {
+                Q.st->stopped = 1;   // a peer never showed up: the host finds the error word
+                return;
+            }
             if (!First) Q.sc[D_PREV_RHO] = Q.sc[D_RHO];
             Q.sc[D_RHO] = Q.sc[D_RED0];
             Q.sc[D_TAU] = sqrt_rn(Q.sc[D_RED1]);
@@ -338,6 +571,7 @@ template <typename V, bool ZisR>
 __global__ void __launch_bounds__(256) dist_cg_direction(DistCgParams<V> P)
 {
     if (P.st->stopped) return;
+    if (P.halo_epoch && blockIdx.x == 0 && threadIdx.x == 0) ++*P.halo_epoch;
     const V prev = P.sc[D_PREV_RHO];
     const bool zero_prev = prev == V(0);
     const V t = zero_prev ? V(0) : div_rn(P.sc[D_RHO], prev);
@@ -367,6 +601,20 @@ struct DistCgSolver : SolverBase<V> {
     gkob200_dist_matrix* dm = nullptr;
     DevBuf vecs, scal, bigws;
     int64_t ws_blocks = 0;
+    // fused path: `chunk` iterations per CUDA graph
+    cudaGraphExec_t graph = nullptr;
+    cudaStream_t cap_stream = nullptr;
+    void* graph_x = nullptr;
+    int64_t launches_per_chunk = 0;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+
+    ~DistCgSolver() override
+    {
+        if (graph) cudaGraphExecDestroy(graph);
+        if (cap_stream) cudaStreamDestroy(cap_stream);
+        for (auto& e : ev)
+            if (e) cudaEventDestroy(e);
+    }
 
     int init()
     {
@@ -380,9 +628,14 @@ struct DistCgSolver : SolverBase<V> {
         if (M.kind != GKOB200_PRECOND_NONE && M.kind != GKOB200_PRECOND_JACOBI_SCALAR) return GKOB200_EUNSUPPORTED;
         if ((rc = vecs.alloc(static_cast<size_t>(n) * 4 * sizeof(V)))) return rc;
         if ((rc = scal.alloc(D_COUNT * sizeof(V)))) return rc;
-        ws_blocks = ceildiv(n, 128) + 1;
+        ws_blocks = ceildiv(n, 128) + sm_count() + 1;   // row blocks + halo push CTAs
         if (ws_blocks < kReduceMaxBlocks) ws_blocks = kReduceMaxBlocks;
-        return bigws.alloc(reduce_ws_bytes(ws_blocks));
+        if ((rc = bigws.alloc(reduce_ws_bytes(ws_blocks)))) return rc;
+        if (dm->fused) {
+            for (auto& e : ev) GKOB200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            GKOB200_CUDA(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
+        }
+        return 0;
     }
 
     DistCgParams<V> params(V* x)
@@ -403,6 +656,7 @@ struct DistCgSolver : SolverBase<V> {
         P.max_iters = stop.max_iters;
         P.ws = bigws.p;
         P.p2p = (dm->comm && dm->comm->p2p) ? dm->comm->p2p_dev_ptr : nullptr;
+        P.halo_epoch = dm->fused ? reinterpret_cast<unsigned long long*>(dm->window + kHaloEpochOff) : nullptr;
         return P;
     }
 
@@ -411,7 +665,7 @@ struct DistCgSolver : SolverBase<V> {
         gkob200_dist_comm* c = dm->comm;
         if (!c || c->size == 1) return 0;
         ++launch_count;
-        return comm_allreduce<V>(c, s, buf, count, &this->st()->stopped);
+        return comm_allreduce<V>(c, s, buf, count, &this->st()->stopped, &this->st()->stopped);
     }
 
     template <bool First>
@@ -434,6 +688,75 @@ struct DistCgSolver : SolverBase<V> {
         return 0;
     }
 
+    // one iteration: direction, distributed SpMV with the fused dot, update
+    int enqueue_iteration(cudaStream_t s, V* x)
+    {
+        DistCgParams<V> P = params(x);
+        const int grid = grid_for(n, 256, 6);
+        if (M.kind == GKOB200_PRECOND_NONE)
+            dist_cg_direction<V, true><<<grid, 256, 0, s>>>(P);
+        else
+            dist_cg_direction<V, false><<<grid, 256, 0, s>>>(P);
+        ++launch_count;
+        GKOB200_CHECK_LAUNCH();
+        SpmvFusion<V> fu;
+        fu.skip = &this->st()->stopped;
+        fu.on_fail = &this->st()->stopped;
+        fu.w = P.p;
+        fu.out = P.sc + D_BETA;
+        fu.ws = bigws.p;
+        fu.ws_blocks = ws_blocks;
+        if (P.p2p) {
+            fu.p2p = P.p2p;
+            fu.p2p_buf = P.sc + D_BETA;
+            fu.p2p_count = dm->fused ? 1 : 2;
+        }
+        int rc;
+        if ((rc = dist_apply<V>(dm, s, P.p, 1, 1, nullptr, nullptr, P.q, 1, &fu, dm->fused))) return rc;
+        // (a rank whose last SpMV could not exchange all-reduces with the stand-alone kernel)
+        if (!dm->exchanged && (rc = allreduce(s, P.sc + D_BETA, dm->fused ? 1 : 2))) return rc;
+        return update<false>(s, x);
+    }
+
+    int build_graph(V* x)
+    {
+        if (graph && graph_x == x) return 0;
+        if (graph) {
+            cudaGraphExecDestroy(graph);
+            graph = nullptr;
+        }
+        const int64_t saved = launch_count, saved_m = dm->launches;
+        cudaGraph_t g = nullptr;
+        GKOB200_CUDA(cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
+        int rc = 0;
+        for (int i = 0; i < this->chunk && rc == 0; ++i) rc = enqueue_iteration(cap_stream, x);
+        cudaError_t e = cudaStreamEndCapture(cap_stream, &g);
+        launches_per_chunk = (launch_count - saved) + (dm->launches - saved_m);
+        launch_count = saved;
+        dm->launches = saved_m;
+        if (rc) {
+            if (g) cudaGraphDestroy(g);
+            return rc;
+        }
+        if (e != cudaSuccess) return static_cast<int>(e);
+        e = cudaGraphInstantiate(&graph, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        graph_x = x;
+        return 0;
+    }
+
+    // sticky error words of the peer-memory exchanges (p2p.cuh)
+    int p2p_error()
+    {
+        gkob200_dist_comm* c = dm->comm;
+        if (!c || !c->p2p) return 0;
+        int err = 0, herr = 0;
+        GKOB200_CUDA(cudaMemcpy(&err, c->p2p_dev.block[c->rank] + kP2pErrorOff, sizeof(int), cudaMemcpyDeviceToHost));
+        if (dm->fused) GKOB200_CUDA(cudaMemcpy(&herr, dm->window + kHaloErrorOff, sizeof(int), cudaMemcpyDeviceToHost));
+        return err ? 2000 : herr ? 2001 : 0;
+    }
+
     int apply(cudaStream_t s, const void* b_, int64_t bs, void* x_, int64_t xs) override
     {
         const V* b = static_cast<const V*>(b_);
@@ -448,7 +771,7 @@ struct DistCgSolver : SolverBase<V> {
         // r = b ; r = -A x + r ; baseline norm (sum of local squared norms, then sqrt:
         // core/distributed/vector.cpp:394-407)
         if ((rc = typed::dense_copy(B::tag(), s, n, int64_t(1), b, int64_t(1), P.r, int64_t(1)))) return rc;
-        if ((rc = typed::dense_fill(B::tag(), s, int64_t(1), int64_t(1), P.sc + D_RHO, int64_t(1), V(0)))) return rc;
+        GKOB200_CUDA(cudaMemsetAsync(P.sc, 0, D_COUNT * sizeof(V), s));
         if ((rc = typed::dense_fill(B::tag(), s, int64_t(1), int64_t(1), P.sc + D_PREV_RHO, int64_t(1), V(1)))) return rc;
         if ((rc = dist_apply<V>(dm, s, x, 1, 1, this->neg_one(), this->one(), P.r, 1, nullptr))) return rc;
         launch_count += 3;
@@ -463,47 +786,43 @@ struct DistCgSolver : SolverBase<V> {
         }
         GKOB200_CHECK_LAUNCH();
         if ((rc = update<true>(s, x))) return rc;
-        int64_t it = 0;
-        bool stopped = false;
-        const int grid = grid_for(n, 256, 6);
-        while (true) {
-            if (it % this->chunk == 0 || it >= stop.max_iters) {
-                if ((rc = this->poll(s, &stopped))) return rc;
-                if (stopped) break;
+        if (dm->fused) {
+            // every rank launches the same number of graphs: the stop flag derives from
+            // all-reduced values, so the pinned copies the hosts read are identical
+            if ((rc = build_graph(x))) return rc;
+            int64_t g = 0;
+            bool done = false;
+            const int64_t max_chunks = ceildiv(stop.max_iters, this->chunk);
+            while (!done) {
+                if (g >= max_chunks) break;
+                GKOB200_CUDA(cudaGraphLaunch(graph, s));
+                launch_count += launches_per_chunk;
+                const int slot = static_cast<int>(g & 1);
+                GKOB200_CUDA(cudaMemcpyAsync(&this->h_state[slot], this->st(), sizeof(SolverState),
+                                             cudaMemcpyDeviceToHost, s));
+                GKOB200_CUDA(cudaEventRecord(ev[slot], s));
+                if (g >= 1) {
+                    GKOB200_CUDA(cudaEventSynchronize(ev[slot ^ 1]));
+                    if (this->h_state[slot ^ 1].stopped) done = true;
+                }
+                ++g;
             }
-            if (M.kind == GKOB200_PRECOND_NONE)
-                dist_cg_direction<V, true><<<grid, 256, 0, s>>>(P);
-            else
-                dist_cg_direction<V, false><<<grid, 256, 0, s>>>(P);
-            ++launch_count;
-            GKOB200_CHECK_LAUNCH();
-            SpmvFusion<V> fu;
-            fu.skip = &this->st()->stopped;
-            fu.w = P.p;
-            fu.out = P.sc + D_BETA;
-            fu.ws = bigws.p;
-            fu.ws_blocks = ws_blocks;
-            if (P.p2p) {
-                fu.p2p = P.p2p;
-                fu.p2p_buf = P.sc + D_BETA;
-                fu.p2p_count = 2;
+            GKOB200_CUDA(cudaStreamSynchronize(s));
+        } else {
+            int64_t it = 0;
+            bool stopped = false;
+            while (true) {
+                if (it % this->chunk == 0 || it >= stop.max_iters) {
+                    if ((rc = this->poll(s, &stopped))) return rc;
+                    if (stopped) break;
+                }
+                if ((rc = enqueue_iteration(s, x))) return rc;
+                ++it;
             }
-            if ((rc = dist_apply<V>(dm, s, P.p, 1, 1, nullptr, nullptr, P.q, 1, &fu))) return rc;
-            // (a rank without a non-local block all-reduces with the stand-alone kernel)
-            if (!dm->exchanged && (rc = allreduce(s, P.sc + D_BETA, 2))) return rc;
-            if ((rc = update<false>(s, x))) return rc;
-            ++it;
         }
         launch_count += dm->launches;
         if ((rc = this->finish(s))) return rc;
-        if (dm->comm && dm->comm->p2p) {
-            // a peer that never showed up in a peer-memory all-reduce (bounded spin)
-            int err = 0;
-            GKOB200_CUDA(cudaMemcpy(&err, dm->comm->p2p_dev.block[dm->comm->rank] + kP2pErrorOff, sizeof(int),
-                                    cudaMemcpyDeviceToHost));
-            if (err) return 2000;
-        }
-        return 0;
+        return p2p_error();
     }
 };
 
@@ -567,9 +886,7 @@ int gkob200_dist_comm_destroy(gkob200_dist_comm* c)
     if (!c) return 0;
     if (c->p2p) {
         cudaDeviceSynchronize();
-        for (int r = 0; r < c->size; ++r)
-            if (r != c->rank && c->p2p_dev.block[r]) cudaIpcCloseMemHandle(c->p2p_dev.block[r]);
-        cudaFree(c->p2p_dev.block[c->rank]);
+        p2p_shared_free(c, c->p2p_dev.block);
         cudaFree(c->p2p_dev_ptr);
     }
     if (c->comm) ncclCommDestroy(c->comm);
@@ -660,13 +977,29 @@ int gkob200_dist_matrix_create(gkob200_dist_comm* comm, const gkob200_matrix* lo
         delete m;
         return static_cast<int>(cudaGetLastError());
     }
+    // collective: every rank of the communicator creates its part of the matrix here
+    const int rc = halo_setup(m);
+    if (rc) {
+        gkob200_dist_matrix_destroy(m);
+        return rc;
+    }
     *out = m;
     return 0;
 }
 
+/* 1 when apply() runs the halo exchange inside the SpMV launch over peer memory (see the file
+ * header); 0: pack + ncclSend/ncclRecv + separate non-local SpMV.  GKOB200_FUSED_HALO=0 in the
+ * environment forces the latter. */
+int gkob200_dist_matrix_uses_fused_halo(const gkob200_dist_matrix* m) { return m && m->fused ? 1 : 0; }
+
 int gkob200_dist_matrix_destroy(gkob200_dist_matrix* m)
 {
     if (!m) return 0;
+    if (m->window) {
+        cudaDeviceSynchronize();
+        p2p_shared_free(m->comm, m->peer_window);
+        m->window = nullptr;
+    }
     if (m->packed) cudaEventDestroy(m->packed);
     if (m->received) cudaEventDestroy(m->received);
     delete m;

@@ -133,9 +133,8 @@ int strided_launch(cudaStream_t s, int64_t n_rows, Fmt fmt, const I* cols, const
 #undef GKOB200_ST
     GKOB200_CHECK_LAUNCH();
     if (fused && fu.out) {
-        finish_partials<V><<<fu.out_sq ? 2 : 1, 1024, 0, s>>>(static_cast<int64_t>(grid), ws_partials<V>(fu.ws), fu.out,
-                                                              fu.skip, fu.out_sq);
-        GKOB200_CHECK_LAUNCH();
+        const int frc = launch_finish_partials<V>(s, static_cast<int64_t>(grid), fu);
+        if (frc) return frc;
     }
     return 0;
 }
@@ -427,11 +426,12 @@ __global__ void __launch_bounds__(256)
         const P2pDev* p2p = static_cast<const P2pDev*>(fu.p2p);
         V* p2p_buf = fu.p2p_buf;
         const int p2p_count = fu.p2p_count;
+        int* on_fail = fu.on_fail;
         grid_reduce<1>(tt, ws_partials<V>(fu.ws), ws_ticket(fu.ws), [=](V(&tot)[1]) {
             out[0] = tot[0];
             // the dot is complete on this rank: all-reduce it right here (one launch for
             // SpMV + dot + all-reduce)
-            if (p2p) peer_allreduce(*p2p, p2p_buf, p2p_count);
+            if (p2p && !peer_allreduce(*p2p, p2p_buf, p2p_count) && on_fail) *on_fail = 1;
         });
     }
 }

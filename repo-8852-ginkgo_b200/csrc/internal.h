@@ -17,13 +17,33 @@ struct SpmvFusion {
     V* out = nullptr;
     V* out_sq = nullptr;    // optional second fused reduction: sum of result^2 (needs `out`)
     // optional: the kernel whose finaliser completes `out` also all-reduces p2p_count values at
-    // p2p_buf over peer memory (p2p.cuh; only the row-compressed non-local SpMV implements it)
+    // p2p_buf over peer memory (p2p.cuh: finish_partials and the row-compressed non-local SpMV);
+    // *on_fail is set to 1 when a peer did not show up (the solver's stopped flag)
     const void* p2p = nullptr;
     V* p2p_buf = nullptr;
     int p2p_count = 0;
+    int* on_fail = nullptr;
+    // optional (CSR row-block kernel, one right-hand side): the halo exchange and the non-local
+    // block of a distributed matrix run inside this launch (device-resident plan, p2p.cuh)
+    const HaloDev* halo = nullptr;
+    int halo_push_ctas = 0;  // host copy of halo->n_push_ctas (extra CTAs at the front of the grid)
     void* ws = nullptr;
     int64_t ws_blocks = 0;  // number of per-block partials `ws` has room for
 };
+
+// second stage of a deferred SpMV reduction (`grid` per-CTA partials per array in fu.ws)
+template <typename V>
+inline int launch_finish_partials(cudaStream_t s, int64_t grid, const SpmvFusion<V>& fu)
+{
+    const int64_t arrays = fu.out_sq ? 2 : 1;
+    if (grid * arrays + 2 * kFinishMaxCtas > (fu.ws_blocks + 256) * kReduceMaxVals) return GKOB200_EWORKSPACE;
+    V* parts = ws_partials<V>(fu.ws);
+    finish_partials<V><<<finish_grid(grid), kFinishThreads, 0, s>>>(
+        grid, parts, fu.out, fu.skip, fu.out_sq, parts + arrays * grid, ws_ticket(fu.ws),
+        static_cast<const P2pDev*>(fu.p2p), fu.p2p_buf, fu.p2p_count, fu.on_fail);
+    GKOB200_CHECK_LAUNCH();
+    return 0;
+}
 
 template <typename V, typename I>
 int csr_spmv_launch(cudaStream_t s, int64_t n_rows, int64_t n_cols, int64_t nnz, const I* row_ptrs,

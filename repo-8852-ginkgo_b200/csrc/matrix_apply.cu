@@ -37,6 +37,9 @@ int matrix_apply(cudaStream_t s, const gkob200_matrix& A, const V* b, int64_t b_
         }
         fp = &fu;
     }
+    // a halo exchange attached to the launch exists in one kernel only; dropping it silently
+    // would drop the non-local part of a distributed matrix
+    if (fusion && fusion->halo && (A.format != GKOB200_FMT_CSR || nrhs != 1)) return GKOB200_EUNSUPPORTED;
     switch (A.format) {
     case GKOB200_FMT_CSR: {
         int strategy = A.csr_strategy;
@@ -44,6 +47,7 @@ int matrix_apply(cudaStream_t s, const gkob200_matrix& A, const V* b, int64_t b_
             strategy = A.csr_max_block_nnz > 0
                            ? gkob200_csr_pick_strategy(A.n_rows, A.nnz, -1, A.csr_max_block_nnz)
                            : GKOB200_CSR_MERGE_PATH;
+        if (fusion && fusion->halo && strategy != GKOB200_CSR_CLASSICAL) return GKOB200_EUNSUPPORTED;
         if ((strategy == GKOB200_CSR_MERGE_PATH || strategy == GKOB200_CSR_MERGE_PATH_PLANNED) && fp) {
             // the merge-path kernel has no skip/dot fusion; its extra work after the
             // solver stopped only touches solver workspace

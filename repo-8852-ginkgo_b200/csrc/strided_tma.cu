@@ -261,9 +261,8 @@ int sellp_spmv_tma_launch(cudaStream_t s, int64_t n_rows, int64_t slice_size, co
 #undef GKOB200_SP
     GKOB200_CHECK_LAUNCH();
     if (fused && fu.out) {
-        finish_partials<V><<<fu.out_sq ? 2 : 1, 1024, 0, s>>>(static_cast<int64_t>(grid), ws_partials<V>(fu.ws), fu.out,
-                                                              fu.skip, fu.out_sq);
-        GKOB200_CHECK_LAUNCH();
+        const int frc = launch_finish_partials<V>(s, static_cast<int64_t>(grid), fu);
+        if (frc) return frc;
     }
     return 1;
 }
@@ -305,9 +304,8 @@ int ell_spmv_tma_launch(cudaStream_t s, int64_t n_rows, int64_t stride, int64_t 
 #undef GKOB200_EL
     GKOB200_CHECK_LAUNCH();
     if (fused && fu.out) {
-        finish_partials<V><<<fu.out_sq ? 2 : 1, 1024, 0, s>>>(static_cast<int64_t>(grid), ws_partials<V>(fu.ws), fu.out,
-                                                              fu.skip, fu.out_sq);
-        GKOB200_CHECK_LAUNCH();
+        const int frc = launch_finish_partials<V>(s, static_cast<int64_t>(grid), fu);
+        if (frc) return frc;
     }
     return 1;
 }

@@ -232,8 +232,9 @@ class Matrix(_SparseBase):
         self.exec, self.comm = exec_, comm
         self._h = None
 
-    def read_distributed(self, rows, cols, vals, row_part, col_part=None):
-        """rows/cols: int64 GLOBAL indices (device or host arrays), row-major sorted."""
+    def read_distributed(self, rows, cols, vals, row_part, col_part=None, local_strategy="automatical"):
+        """rows/cols: int64 GLOBAL indices (device or host arrays), row-major sorted.
+        Collective over the communicator (every rank reads its part)."""
         exec_, comm = self.exec, self.comm
         col_part = col_part or row_part
         dev = exec_.device
@@ -243,7 +244,7 @@ class Matrix(_SparseBase):
         self.size = (row_part.size, col_part.size)
         n_loc_rows, n_loc_cols = row_part.get_part_size(comm.rank), col_part.get_part_size(comm.rank)
         n_ghost = parts["gather"].numel()
-        self.local = _coo_to_csr(exec_, n_loc_rows, n_loc_cols, parts["lrow"], parts["lcol"], parts["lval"], "automatical")
+        self.local = _coo_to_csr(exec_, n_loc_rows, n_loc_cols, parts["lrow"], parts["lcol"], parts["lval"], local_strategy)
         # non-local block: same entries as the reference's Csr non_local_mtx_, stored row-compressed
         self.non_local = CsrRows(exec_, (n_loc_rows, n_ghost), parts["nrow"], parts["ncol"], parts["nval"])
         self.non_local_to_global = parts["nl_to_global"]
@@ -260,6 +261,11 @@ class Matrix(_SparseBase):
         h, self._h = getattr(self, "_h", None), None
         if h and lib is not None:  # lib is None while the interpreter shuts down
             lib.gkob200_dist_matrix_destroy(h)
+
+    @property
+    def uses_fused_halo(self):
+        """apply() is one launch: halo push over peer memory + local + non-local rows"""
+        return bool(lib.gkob200_dist_matrix_uses_fused_halo(self._h))
 
     def apply(self, *args):
         """b, x are the LOCAL parts (Dense) of the distributed vectors."""

@@ -80,13 +80,20 @@ def test_single_rank_distributed_matrix_and_cg(gko, exec_, ora):
     assert np.isclose(res.to_numpy()[0, 0], np.linalg.norm(b), rtol=1e-14)
 
 
+# exchange paths: everything over peer memory inside the kernels (default), peer-memory scalar
+# all-reduce + NCCL halo, everything on NCCL
+PATHS = {"fused-halo": {}, "p2p-allreduce+nccl-halo": {"GKOB200_FUSED_HALO": "0"}, "nccl": {"GKOB200_P2P": "0"}}
+
+
+@pytest.mark.parametrize("path", list(PATHS))
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_multi_gpu_torchrun(world):
+def test_multi_gpu_torchrun(world, path):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs (run with gpurun --gpus {world})")
-    port = 29600 + world
+    port = 29600 + world + 16 * list(PATHS).index(path)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist_worker.py")]
-    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    env = dict(os.environ, GKOB200_P2P_TIMEOUT_MS="20000", **PATHS[path])
+    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900, env=env)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert f"DIST_OK world={world}" in out.stdout
+    assert f"DIST_OK world={world} path={path}" in out.stdout, out.stdout[-2000:]
