@@ -135,10 +135,14 @@ def verify_reduced(gko, exec_, kind, g, planes, rank, world, dist, torch, log):
         b.fill(1.0)
         x = gko.matrix.Dense.create(exec_, (hi - lo, 1))
         s.apply(b, x)
+        first = (int(s.num_iterations), np.asarray(s.residual_history[:nh], dtype=np.float64))
+        x.fill(0.0)
+        s.apply(b, x)      # a second solve on the same solver object must repeat the first one
         hist = np.asarray(s.residual_history[:nh], dtype=np.float64)
+        repeat_ok = first[0] == int(s.num_iterations) and np.array_equal(first[1], hist)
         hist_err = float(np.max(np.abs(hist - hist_ref[:len(hist)]) / hist_ref[:len(hist)])) if len(hist) else 0.0
         x_err = float((x.t[:, 0] - xg[lo:hi]).abs().max().item() / xg.abs().max().item())
-        bad = (abs(s.num_iterations - it_ref) > 2) or len(hist) != nh or hist_err > 1e-10 or x_err > 1e-8
+        bad = (abs(s.num_iterations - it_ref) > 2) or len(hist) != nh or hist_err > 1e-10 or x_err > 1e-8 or not repeat_ok
         flags = torch.tensor([float(bad), hist_err, x_err], dtype=torch.float64, device=exec_.device)
         dist.all_reduce(flags, op=dist.ReduceOp.MAX)
         result["paths"][name] = {"ran": ran, "iterations": int(s.num_iterations), "max_rel_err_first_10_residual_norms":
@@ -248,13 +252,18 @@ def run_distributed(args, gko, rank, world, local_rank):
         dist.barrier()
         return float(t.item()), launches
 
-    for _ in range(max(args.warmup, 3)):
+    step_device()
+    hist_first = np.asarray(solver.residual_history[:10], dtype=np.float64)
+    for _ in range(max(args.warmup, 3) - 1):
         step_device()
     sampler.mark()
     secs, launches = timed(step_device, args.steps)
     clocks = sampler.stop()
     assert solver.num_iterations == iters
     hist_head = [float(v) for v in solver.residual_history[:10]]
+    # every timed solve is the same solve: its residual norms must repeat the first one's and move
+    if not np.array_equal(hist_first, np.asarray(hist_head)) or (len(hist_head) > 2 and hist_head[1] == hist_head[0]):
+        raise SystemExit(f"timed solves do not repeat the first solve: {hist_first} vs {hist_head}")
     slabs = world if args.scaling == "weak" else 1
     value = slabs * args.steps * iters / secs
     for _ in range(2):

@@ -128,7 +128,8 @@ __global__ void __launch_bounds__(kRowsPerCta)
 // scheduled.
 // ---------------------------------------------------------------------------
 template <typename V>
-__device__ __forceinline__ void halo_push_cta(const HaloDev* __restrict__ H, const V* __restrict__ b, int64_t b_stride)
+__device__ __forceinline__ void halo_push_cta(const HaloDev* __restrict__ H, const V* __restrict__ b, int64_t b_stride,
+                                              int* on_fail)
 {
     const int tid = threadIdx.x;
     unsigned char* win = H->window;
@@ -148,7 +149,10 @@ __device__ __forceinline__ void halo_push_cta(const HaloDev* __restrict__ H, con
     __syncthreads();
     if (s_fail) {
         // never publish `arrived`: the receivers time out as well and every rank reports the error
-        if (tid == 0) *reinterpret_cast<volatile int*>(win + kHaloErrorOff) = 1;
+        if (tid == 0) {
+            *reinterpret_cast<volatile int*>(win + kHaloErrorOff) = 1;
+            if (on_fail) *on_fail = 1;
+        }
         return;
     }
     // (3) this CTA's share of the send list
@@ -201,22 +205,32 @@ __global__ void __launch_bounds__(kRowsPerCta)
     int64_t blk = blockIdx.x;
     int nl_slot = -1;   // >= 0: this CTA owns rows with non-local entries (index into nl_slot_begin)
     if (Halo) {
-        const HaloDev* __restrict__ H = fu.halo;
-        if (fu.skip && *fu.skip) return;   // uniform (push CTAs included: no rank pushes after the stop)
-        const int n_push = H->n_push_ctas;
+        const int n_push = fu.halo_push_ctas;
         if (static_cast<int>(blockIdx.x) < n_push) {
-            halo_push_cta<V>(H, b, b_stride);
+            if (fu.skip && *fu.skip) return;   // no rank pushes after the stop (the flag is global)
+            halo_push_cta<V>(fu.halo, b, b_stride, fu.on_fail);
             if (Fused && fu.out && tid == 0) {   // the deferred reduction reads one partial per CTA
                 ws_partials<V>(fu.ws)[blockIdx.x] = V(0);
                 if (fu.out_sq) ws_partials<V>(fu.ws)[gridDim.x + blockIdx.x] = V(0);
             }
             return;
         }
-        // interior row blocks first, blocks with non-local rows last: by the time they run the
-        // neighbours' entries have normally arrived and nobody spins
+        // Interior row blocks first, blocks with non-local rows last: by the time they run the
+        // neighbours' entries have normally arrived and nobody spins.  The interior mapping is
+        // arithmetic on kernel parameters: nothing is loaded in front of the bulk copy.
         const int slot = static_cast<int>(blockIdx.x) - n_push;
-        blk = H->order[slot];
-        if (slot >= H->n_interior) nl_slot = slot - H->n_interior;
+        if (slot >= fu.halo_n_interior) {
+            nl_slot = slot - fu.halo_n_interior;
+            blk = fu.halo->order[slot];
+        } else if (fu.halo_runs > 0) {
+            int r = 0;
+#pragma unroll
+            for (int i = 1; i < kHaloRuns; ++i)
+                if (i < fu.halo_runs && slot >= fu.halo_run_slot[i]) r = i;
+            blk = fu.halo_run_block[r] + (slot - fu.halo_run_slot[r]);
+        } else {
+            blk = fu.halo->order[slot];
+        }
     }
     const int64_t row0 = blk * kRowsPerCta;
     const int nrow = static_cast<int>(min(static_cast<int64_t>(kRowsPerCta), n_rows - row0));
@@ -320,6 +334,7 @@ __global__ void __launch_bounds__(kRowsPerCta)
             if (!wait_flag_ge(f, e, H->timeout_ns)) {
                 s_wait_ok = 0;
                 *reinterpret_cast<volatile int*>(win + kHaloErrorOff) = 1;
+                if (fu.on_fail) *fu.on_fail = 1;
             }
         }
         const int j0 = H->nl_slot_begin[nl_slot], j1 = H->nl_slot_begin[nl_slot + 1];

@@ -69,7 +69,8 @@ struct gkob200_dist_matrix {
     unsigned char* window = nullptr;                  // local window (cudaMalloc)
     unsigned char* peer_window[kP2pMaxRanks] = {};    // IPC mappings (peer_window[rank] == window)
     gkob200::DevBuf halo_dev, order, nl_slot_begin;
-    int n_push = 0;
+    int n_push = 0, n_interior = 0, n_runs = 0;
+    int run_slot[gkob200::kHaloRuns + 1] = {}, run_block[gkob200::kHaloRuns] = {};
 };
 
 namespace gkob200 {
@@ -343,6 +344,25 @@ int halo_setup(gkob200_dist_matrix* m)
     for (int64_t b = 0; b < n_blocks; ++b)
         if (!is_boundary[b]) order.push_back(static_cast<int32_t>(b));
     H.n_interior = static_cast<int>(order.size());
+    m->n_interior = H.n_interior;
+    // interior slots as runs of consecutive blocks (slab partitions: one run; <= kHaloRuns runs
+    // travel in the kernel parameters, otherwise the kernel looks the slot up in `order`)
+    {
+        std::vector<int> rs, rb;
+        for (size_t sl = 0; sl < order.size(); ++sl)
+            if (sl == 0 || order[sl] != order[sl - 1] + 1) {
+                rs.push_back(static_cast<int>(sl));
+                rb.push_back(order[sl]);
+            }
+        if (!rs.empty() && rs.size() <= static_cast<size_t>(kHaloRuns)) {
+            m->n_runs = static_cast<int>(rs.size());
+            for (int i = 0; i < m->n_runs; ++i) {
+                m->run_slot[i] = rs[i];
+                m->run_block[i] = rb[i];
+            }
+            m->run_slot[m->n_runs] = H.n_interior;
+        }
+    }
     order.insert(order.end(), boundary.begin(), boundary.end());
     if ((rc = m->order.alloc(order.size() * sizeof(int32_t) + 16))) return rc;
     if ((rc = m->nl_slot_begin.alloc(slot_begin.size() * sizeof(int32_t) + 16))) return rc;
@@ -411,6 +431,13 @@ int dist_apply(gkob200_dist_matrix* m, cudaStream_t s, const V* b, int64_t bs, i
         }
         fu.halo = m->halo_dev.as<HaloDev>();
         fu.halo_push_ctas = m->n_push;
+        fu.halo_n_interior = m->n_interior;
+        fu.halo_runs = m->n_runs;
+        for (int i = 0; i < kHaloRuns; ++i) {
+            fu.halo_run_slot[i] = m->run_slot[i];
+            fu.halo_run_block[i] = m->run_block[i];
+        }
+        fu.halo_run_slot[kHaloRuns] = m->run_slot[kHaloRuns];
         m->exchanged = fu.out != nullptr && fu.p2p != nullptr;
         if ((rc = matrix_apply<V>(s, m->local, b, bs, 1, alpha, beta, x, xs, &fu))) return rc;
         m->launches += fu.out ? 2 : 1;
@@ -768,9 +795,16 @@ struct DistCgSolver : SolverBase<V> {
         DistCgParams<V> P = params(x);
         int rc;
         if ((rc = this->reset_state(s))) return rc;
+        // stopping_status starts cleared on every apply (cg::initialize does it in the reference,
+        // reference/solver/cg_kernels.cpp:60-63): a converged status left by an earlier apply on
+        // this solver object would end the new solve at iteration 0
+        GKOB200_CUDA(cudaMemsetAsync(this->stat(), 0, static_cast<size_t>(k), s));
+        // z = p = q = 0 (cg::initialize): the first direction update is p = z + rho * p_old and
+        // must not see the previous solve's p
         // r = b ; r = -A x + r ; baseline norm (sum of local squared norms, then sqrt:
         // core/distributed/vector.cpp:394-407)
         if ((rc = typed::dense_copy(B::tag(), s, n, int64_t(1), b, int64_t(1), P.r, int64_t(1)))) return rc;
+        GKOB200_CUDA(cudaMemsetAsync(P.z, 0, static_cast<size_t>(n) * 3 * sizeof(V), s));
         GKOB200_CUDA(cudaMemsetAsync(P.sc, 0, D_COUNT * sizeof(V), s));
         if ((rc = typed::dense_fill(B::tag(), s, int64_t(1), int64_t(1), P.sc + D_PREV_RHO, int64_t(1), V(1)))) return rc;
         if ((rc = dist_apply<V>(dm, s, x, 1, 1, this->neg_one(), this->one(), P.r, 1, nullptr))) return rc;

@@ -10,6 +10,8 @@ namespace gkob200 {
 //         has stopped — mirrors the reference's per-column has_stopped() guards)
 //  w/out: additionally compute out[0] = sum_i w[i] * (A b)[i] in the same pass
 //         (single-pass grid reduction through `ws`)
+constexpr int kHaloRuns = 4;
+
 template <typename V>
 struct SpmvFusion {
     const int* skip = nullptr;
@@ -27,6 +29,14 @@ struct SpmvFusion {
     // block of a distributed matrix run inside this launch (device-resident plan, p2p.cuh)
     const HaloDev* halo = nullptr;
     int halo_push_ctas = 0;  // host copy of halo->n_push_ctas (extra CTAs at the front of the grid)
+    // CTA slot -> row block for the interior slots, as up to kHaloRuns runs of consecutive blocks
+    // held in the kernel parameters (no dependent load in front of the bulk copy): run i covers
+    // slots [halo_run_slot[i], halo_run_slot[i+1]) -> blocks halo_run_block[i] + (slot - ...).
+    // halo_runs == 0: look the slot up in halo->order (scattered boundary rows).
+    int halo_n_interior = 0;
+    int halo_runs = 0;
+    int halo_run_slot[kHaloRuns + 1] = {};
+    int halo_run_block[kHaloRuns] = {};
     void* ws = nullptr;
     int64_t ws_blocks = 0;  // number of per-block partials `ws` has room for
 };
