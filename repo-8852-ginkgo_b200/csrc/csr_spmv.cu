@@ -235,6 +235,22 @@ __global__ void __launch_bounds__(kRowsPerCta)
     const int64_t row0 = blk * kRowsPerCta;
     const int nrow = static_cast<int>(min(static_cast<int64_t>(kRowsPerCta), n_rows - row0));
     if (tid == 0) mbar_init(&bar, 1);
+    // Boundary CTA: everything the non-local tail needs is requested NOW, so that its load
+    // latencies hide behind the local tile (the tail then costs one gather, not a chain of six)
+    int nl_k0 = 0, nl_k1 = 0;
+    unsigned long long halo_epoch = 0, halo_seen = 0;
+    if (Halo && nl_slot >= 0) {
+        const HaloDev* __restrict__ H = fu.halo;
+        const int j = H->nl_thread_row[nl_slot * kRowsPerCta + tid];
+        if (j >= 0) {
+            nl_k0 = H->nl_row_ptrs[j];
+            nl_k1 = H->nl_row_ptrs[j + 1];
+        }
+        halo_epoch = *reinterpret_cast<const unsigned long long*>(H->window + kHaloEpochOff);
+        if (tid < H->n_recv_peers)
+            halo_seen = ld_acquire_sys(reinterpret_cast<const unsigned long long*>(H->window + kHaloArrivedOff) +
+                                       H->recv_peer[tid]);
+    }
     // Independent loads issued back to back so that their latencies overlap: the solver's
     // "stopped" flag, this thread's two row pointers (coalesced, overlapping by one) and —
     // for the fused dot — w[row], which is only needed in the epilogue.
@@ -321,32 +337,24 @@ __global__ void __launch_bounds__(kRowsPerCta)
         // result is bit-identical to two separate applies.
         const HaloDev* __restrict__ H = fu.halo;
         unsigned char* win = H->window;
-        __shared__ int s_wait_ok;
-        __syncthreads();   // everyone is done with the staged tile: its space becomes the row map
-        int* s_nl = reinterpret_cast<int*>(smem_raw);
-        s_nl[tid] = -1;
-        if (tid == 0) s_wait_ok = 1;
+        __shared__ int s_wait_fail;
+        if (tid == 0) s_wait_fail = 0;
         __syncthreads();
-        const unsigned long long e = *reinterpret_cast<const unsigned long long*>(win + kHaloEpochOff);
-        if (tid < H->n_recv_peers) {
+        if (tid < H->n_recv_peers && halo_seen < halo_epoch) {
             const unsigned long long* f =
                 reinterpret_cast<const unsigned long long*>(win + kHaloArrivedOff) + H->recv_peer[tid];
-            if (!wait_flag_ge(f, e, H->timeout_ns)) {
-                s_wait_ok = 0;
+            if (!wait_flag_ge(f, halo_epoch, H->timeout_ns)) {
+                s_wait_fail = 1;
                 *reinterpret_cast<volatile int*>(win + kHaloErrorOff) = 1;
                 if (fu.on_fail) *fu.on_fail = 1;
             }
         }
-        const int j0 = H->nl_slot_begin[nl_slot], j1 = H->nl_slot_begin[nl_slot + 1];
-        for (int j = j0 + tid; j < j1; j += kRowsPerCta) s_nl[H->nl_row_list[j] - row0] = j;
         __syncthreads();
-        const int j = s_nl[tid];
-        if (j >= 0 && s_wait_ok) {
+        if (nl_k1 > nl_k0 && !s_wait_fail) {
             // (L2 loads: the window is written by the peers, never through this SM's L1)
-            const V* recv = reinterpret_cast<const V*>(win + kHaloDataOff) + (e & 1) * H->recv_stride;
+            const V* recv = reinterpret_cast<const V*>(win + kHaloDataOff) + (halo_epoch & 1) * H->recv_stride;
             const V* nl_vals = static_cast<const V*>(H->nl_vals);
-            const int k1 = H->nl_row_ptrs[j + 1];
-            for (int k = H->nl_row_ptrs[j]; k < k1; ++k) {
+            for (int k = nl_k0; k < nl_k1; ++k) {
                 const V v = Advanced ? mul_rn(alpha, nl_vals[k]) : nl_vals[k];
                 acc = add_rn(acc, mul_rn(v, __ldcg(recv + H->nl_cols[k])));
             }

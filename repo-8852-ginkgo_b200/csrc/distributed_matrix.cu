@@ -68,7 +68,7 @@ struct gkob200_dist_matrix {
     bool fused = false;
     unsigned char* window = nullptr;                  // local window (cudaMalloc)
     unsigned char* peer_window[kP2pMaxRanks] = {};    // IPC mappings (peer_window[rank] == window)
-    gkob200::DevBuf halo_dev, order, nl_slot_begin;
+    gkob200::DevBuf halo_dev, order, nl_thread_row;
     int n_push = 0, n_interior = 0, n_runs = 0;
     int run_slot[gkob200::kHaloRuns + 1] = {}, run_block[gkob200::kHaloRuns] = {};
 };
@@ -328,18 +328,18 @@ int halo_setup(gkob200_dist_matrix* m)
     if (!row_list.empty())
         GKOB200_CUDA(cudaMemcpy(row_list.data(), m->non_local.row_list, row_list.size() * sizeof(int32_t),
                                 cudaMemcpyDeviceToHost));
-    std::vector<int32_t> order, slot_begin, boundary;
+    std::vector<int32_t> order, boundary, thread_row;
     std::vector<char> is_boundary(static_cast<size_t>(n_blocks), 0);
     for (size_t j = 0; j < row_list.size(); ++j) {
         const int32_t blk = row_list[j] / 128;
         if (blk < 0 || blk >= n_blocks || (j > 0 && row_list[j] <= row_list[j - 1])) return GKOB200_EINVAL;
         if (boundary.empty() || boundary.back() != blk) {
             boundary.push_back(blk);
-            slot_begin.push_back(static_cast<int32_t>(j));
+            thread_row.resize(boundary.size() * 128, -1);
             is_boundary[blk] = 1;
         }
+        thread_row[(boundary.size() - 1) * 128 + static_cast<size_t>(row_list[j] % 128)] = static_cast<int32_t>(j);
     }
-    slot_begin.push_back(static_cast<int32_t>(row_list.size()));
     order.reserve(static_cast<size_t>(n_blocks));
     for (int64_t b = 0; b < n_blocks; ++b)
         if (!is_boundary[b]) order.push_back(static_cast<int32_t>(b));
@@ -365,13 +365,13 @@ int halo_setup(gkob200_dist_matrix* m)
     }
     order.insert(order.end(), boundary.begin(), boundary.end());
     if ((rc = m->order.alloc(order.size() * sizeof(int32_t) + 16))) return rc;
-    if ((rc = m->nl_slot_begin.alloc(slot_begin.size() * sizeof(int32_t) + 16))) return rc;
+    if ((rc = m->nl_thread_row.alloc(thread_row.size() * sizeof(int32_t) + 16))) return rc;
     GKOB200_CUDA(cudaMemcpy(m->order.p, order.data(), order.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-    GKOB200_CUDA(cudaMemcpy(m->nl_slot_begin.p, slot_begin.data(), slot_begin.size() * sizeof(int32_t),
-                            cudaMemcpyHostToDevice));
+    if (!thread_row.empty())
+        GKOB200_CUDA(cudaMemcpy(m->nl_thread_row.p, thread_row.data(), thread_row.size() * sizeof(int32_t),
+                                cudaMemcpyHostToDevice));
     H.order = m->order.as<int32_t>();
-    H.nl_slot_begin = m->nl_slot_begin.as<int32_t>();
-    H.nl_row_list = m->non_local.row_list;
+    H.nl_thread_row = m->nl_thread_row.as<int32_t>();
     H.nl_row_ptrs = static_cast<const int32_t*>(m->non_local.row_ptrs);
     H.nl_cols = static_cast<const int32_t*>(m->non_local.col_idxs);
     H.nl_vals = m->non_local.values;

@@ -13,11 +13,14 @@
 // Every wait is bounded by a wall-clock timeout (globaltimer); a rank that gives up raises a
 // sticky error word that the host reads at every poll.
 //
-// Scalar block (4 KB per rank):
-//   slots  double[2][kP2pMaxRanks][4]   values written BY rank r INTO everybody's block
-//   flags  u64   [2][kP2pMaxRanks]      epoch of the last complete write of rank r
-//   epoch  u64                          number of all-reduces done (local)
-//   error  int                          set when a peer did not show up in time
+// Scalar block (4 KB per rank), written in the style of NCCL's LL protocol — every 8-byte word
+// carries 4 bytes of payload and the 32-bit epoch tag, so a word is either old or complete and
+// NO fence / flag round trip is needed (one NVLink one-way latency per all-reduce instead of a
+// store, a system fence round trip and a flag store):
+//   slots  u64[2][kP2pMaxRanks][8]   value c of rank r = words 2c (low half | tag << 32) and
+//                                    2c+1 (high half | tag << 32), written BY r INTO everybody's block
+//   epoch  u64                       number of all-reduces done (local)
+//   error  int                       set when a peer did not show up in time
 // Double-buffered by epoch parity: a rank can be at most one all-reduce ahead of a peer.
 #pragma once
 #include <cstdint>
@@ -25,9 +28,9 @@
 namespace gkob200 {
 
 constexpr int kP2pMaxRanks = 16;
-constexpr size_t kP2pSlotsOff = 0, kP2pFlagsOff = 2 * kP2pMaxRanks * 4 * sizeof(double),
-                 kP2pEpochOff = kP2pFlagsOff + 2 * kP2pMaxRanks * sizeof(unsigned long long),
+constexpr size_t kP2pSlotsOff = 0, kP2pEpochOff = 2 * kP2pMaxRanks * 8 * sizeof(unsigned long long),
                  kP2pErrorOff = kP2pEpochOff + 8, kP2pBlockBytes = 4096;
+static_assert(kP2pErrorOff + 4 <= kP2pBlockBytes, "scalar block layout");
 
 struct P2pDev {
     int rank, size;
@@ -65,9 +68,16 @@ __device__ __forceinline__ bool wait_flag_ge(const unsigned long long* flag, uns
     return true;
 }
 
-// ONE thread: push my `count` (<= 4) values into every rank's block, publish the epoch with a
-// system-scope release, wait for every rank's epoch in my own block, sum in rank order (the
-// same order on every rank: identical bits everywhere, run-to-run reproducible).
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// ONE thread: store my `count` (<= 4) values, tagged with the epoch, into every rank's block;
+// wait until every rank's tagged words for this epoch stand in my own block; sum in rank order
+// (the same order on every rank: identical bits everywhere, run-to-run reproducible).
 // Returns false (and raises the block's error word) when a peer did not show up in time; the
 // caller must then stop the solve on this rank (the values in `buf` are a partial sum).
 template <typename V>
@@ -77,33 +87,39 @@ __device__ __forceinline__ bool peer_allreduce(const P2pDev& pr, V* buf, int cou
     unsigned long long* epoch = reinterpret_cast<unsigned long long*>(mine + kP2pEpochOff);
     const unsigned long long e = *epoch + 1;
     const int parity = static_cast<int>(e & 1);
-    double v[4];
-    for (int c = 0; c < 4; ++c) v[c] = c < count ? static_cast<double>(buf[c]) : 0.0;
-    for (int r = 0; r < pr.size; ++r) {
-        volatile double* dst = reinterpret_cast<volatile double*>(pr.block[r] + kP2pSlotsOff) +
-                               (parity * kP2pMaxRanks + pr.rank) * 4;
-        for (int c = 0; c < count; ++c) dst[c] = v[c];
+    const unsigned long long tag = (e & 0xffffffffull) << 32;
+    unsigned long long w[8];
+    for (int c = 0; c < 4; ++c) {
+        const unsigned long long bits =
+            c < count ? static_cast<unsigned long long>(__double_as_longlong(static_cast<double>(buf[c]))) : 0ull;
+        w[2 * c] = (bits & 0xffffffffull) | tag;
+        w[2 * c + 1] = (bits >> 32) | tag;
     }
-    // ONE system-scope fence orders all the value stores before all the flag stores (a release
-    // store per flag would wait for an NVLink round trip eight times: 25 us instead of 5)
-    __threadfence_system();
     for (int r = 0; r < pr.size; ++r) {
-        unsigned long long* f = reinterpret_cast<unsigned long long*>(pr.block[r] + kP2pFlagsOff) +
-                                parity * kP2pMaxRanks + pr.rank;
-        st_relaxed_sys(f, e);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(pr.block[r] + kP2pSlotsOff) +
+                                  (parity * kP2pMaxRanks + pr.rank) * 8;
+        for (int i = 0; i < 2 * count; ++i) st_relaxed_sys(dst + i, w[i]);
     }
     double tot[4] = {0.0, 0.0, 0.0, 0.0};
     bool ok = true;
+    const unsigned long long t0 = global_timer_ns();
     for (int r = 0; r < pr.size; ++r) {
-        const unsigned long long* f = reinterpret_cast<const unsigned long long*>(mine + kP2pFlagsOff) +
-                                      parity * kP2pMaxRanks + r;
-        if (ok && !wait_flag_ge(f, e, pr.timeout_ns)) {
-            ok = false;
-            *reinterpret_cast<volatile int*>(mine + kP2pErrorOff) = 1;
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(mine + kP2pSlotsOff) +
+                                        (parity * kP2pMaxRanks + r) * 8;
+        for (int c = 0; c < count; ++c) {
+            unsigned long long lo = ld_relaxed_sys(src + 2 * c), hi = ld_relaxed_sys(src + 2 * c + 1);
+            unsigned spins = 0;
+            while (ok && ((lo ^ tag) >> 32 || (hi ^ tag) >> 32)) {
+                if ((++spins & 0x3ffu) == 0 && global_timer_ns() - t0 > pr.timeout_ns) {
+                    ok = false;
+                    *reinterpret_cast<volatile int*>(mine + kP2pErrorOff) = 1;
+                    break;
+                }
+                lo = ld_relaxed_sys(src + 2 * c);
+                hi = ld_relaxed_sys(src + 2 * c + 1);
+            }
+            tot[c] += __longlong_as_double(static_cast<long long>((lo & 0xffffffffull) | (hi << 32)));
         }
-        const volatile double* src = reinterpret_cast<const volatile double*>(mine + kP2pSlotsOff) +
-                                     (parity * kP2pMaxRanks + r) * 4;
-        for (int c = 0; c < count; ++c) tot[c] += src[c];
     }
     for (int c = 0; c < count; ++c) buf[c] = static_cast<V>(tot[c]);
     *epoch = e;
@@ -148,8 +164,8 @@ struct HaloDev {
     long long recv_stride;                    // values between my two receive buffers
     // ---- non-local block (row-compressed) and the CTA order ----
     const int* order;                         // slot -> row block; boundary blocks last
-    const int* nl_slot_begin;                 // boundary slot j: listed rows [nl_slot_begin[j], nl_slot_begin[j+1])
-    const int* nl_row_list;
+    const int* nl_thread_row;                 // boundary slot j, thread t: index of row (block*128 + t) in the
+                                              // row-compressed non-local block, or -1  [128 per slot]
     const int* nl_row_ptrs;
     const int* nl_cols;
     const void* nl_vals;
