@@ -186,8 +186,14 @@ __device__ __forceinline__ void halo_push_cta(const HaloDev* __restrict__ H, con
     }
 }
 
+// Resident CTAs per SM the register allocation must allow.  Short-row matrices (5-pt / 7-pt:
+// ~10 KB tiles) are limited by registers, not shared memory, and the kernel needs every resident
+// tile it can get to cover HBM latency: 12 CTAs (<= 40 registers) instead of the 10 that the
+// fused / halo variants got at 44-48 registers cost 20 % of the bandwidth.
+constexpr int rowblock_min_ctas(int batch, size_t) { return batch <= 7 ? 12 : batch <= 9 ? 9 : 1; }
+
 template <typename V, typename I, bool Advanced, bool Fused, int kBatch, bool Halo = false>
-__global__ void __launch_bounds__(kRowsPerCta)
+__global__ void __launch_bounds__(kRowsPerCta, rowblock_min_ctas(kBatch, sizeof(V)))
     csr_spmv_rowblock_tma(int64_t n_rows, const I* __restrict__ row_ptrs, const I* __restrict__ col_idxs,
                           const V* __restrict__ values, const V* __restrict__ b, int64_t b_stride,
                           const V* __restrict__ alpha_p, const V* __restrict__ beta_p, V* __restrict__ c,
@@ -235,22 +241,8 @@ __global__ void __launch_bounds__(kRowsPerCta)
     const int64_t row0 = blk * kRowsPerCta;
     const int nrow = static_cast<int>(min(static_cast<int64_t>(kRowsPerCta), n_rows - row0));
     if (tid == 0) mbar_init(&bar, 1);
-    // Boundary CTA: everything the non-local tail needs is requested NOW, so that its load
-    // latencies hide behind the local tile (the tail then costs one gather, not a chain of six)
-    int nl_k0 = 0, nl_k1 = 0;
-    unsigned long long halo_epoch = 0, halo_seen = 0;
-    if (Halo && nl_slot >= 0) {
-        const HaloDev* __restrict__ H = fu.halo;
-        const int j = H->nl_thread_row[nl_slot * kRowsPerCta + tid];
-        if (j >= 0) {
-            nl_k0 = H->nl_row_ptrs[j];
-            nl_k1 = H->nl_row_ptrs[j + 1];
-        }
-        halo_epoch = *reinterpret_cast<const unsigned long long*>(H->window + kHaloEpochOff);
-        if (tid < H->n_recv_peers)
-            halo_seen = ld_acquire_sys(reinterpret_cast<const unsigned long long*>(H->window + kHaloArrivedOff) +
-                                       H->recv_peer[tid]);
-    }
+    int nl_k0 = 0, nl_k1 = 0;   // boundary CTA: this thread's entries of the non-local block
+    unsigned long long halo_epoch = 0;
     // Independent loads issued back to back so that their latencies overlap: the solver's
     // "stopped" flag, this thread's two row pointers (coalesced, overlapping by one) and —
     // for the fused dot — w[row], which is only needed in the epilogue.
@@ -304,6 +296,15 @@ __global__ void __launch_bounds__(kRowsPerCta)
             if (tid >= 32 && tid < 32 + IA && ct + (tid - 32) < chunk_end)
                 s_col[ct + (tid - 32) - cb] = col_idxs[ct + (tid - 32)];
         }
+        if (Halo && nl_slot >= 0 && chunk == tile_begin) {
+            // Boundary CTA: what the non-local tail needs is requested while the bulk copy of
+            // the local tile is in flight (one coalesced load per thread)
+            const HaloDev* __restrict__ H = fu.halo;
+            const int2 range = H->nl_thread_range[nl_slot * kRowsPerCta + tid];
+            nl_k0 = range.x;
+            nl_k1 = range.y;
+            halo_epoch = *reinterpret_cast<const unsigned long long*>(H->window + kHaloEpochOff);
+        }
         mbar_wait(&bar, parity);
         parity ^= 1u;
         __syncthreads();  // tails visible
@@ -340,7 +341,8 @@ __global__ void __launch_bounds__(kRowsPerCta)
         __shared__ int s_wait_fail;
         if (tid == 0) s_wait_fail = 0;
         __syncthreads();
-        if (tid < H->n_recv_peers && halo_seen < halo_epoch) {
+        if (tid < H->n_recv_peers) {
+            // (acquire even when the peek already saw the flag: the entries are read next)
             const unsigned long long* f =
                 reinterpret_cast<const unsigned long long*>(win + kHaloArrivedOff) + H->recv_peer[tid];
             if (!wait_flag_ge(f, halo_epoch, H->timeout_ns)) {

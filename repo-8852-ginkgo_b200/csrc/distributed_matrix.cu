@@ -68,7 +68,7 @@ struct gkob200_dist_matrix {
     bool fused = false;
     unsigned char* window = nullptr;                  // local window (cudaMalloc)
     unsigned char* peer_window[kP2pMaxRanks] = {};    // IPC mappings (peer_window[rank] == window)
-    gkob200::DevBuf halo_dev, order, nl_thread_row;
+    gkob200::DevBuf halo_dev, order, nl_thread_range;
     int n_push = 0, n_interior = 0, n_runs = 0;
     int run_slot[gkob200::kHaloRuns + 1] = {}, run_block[gkob200::kHaloRuns] = {};
 };
@@ -234,6 +234,15 @@ int comm_allreduce(gkob200_dist_comm* c, cudaStream_t s, V* buf, size_t count, c
     return 0;
 }
 
+// Measurement-only switches (tools/dist_ab.py; results are WRONG with any bit set):
+//   bit 0: do not enter a new halo epoch (no rank ever waits for a neighbour)
+//   bit 1: skip the scalar all-reduces of the distributed CG
+inline int dist_debug()
+{
+    const char* e = getenv("GKOB200_DIST_DEBUG");
+    return e ? atoi(e) : 0;
+}
+
 // ---- fused halo: plan ------------------------------------------------------------------
 // true when matrix_apply runs this descriptor on the bulk-async CSR row-block kernel with
 // 32-bit indices (the only kernel that carries the halo exchange)
@@ -328,17 +337,22 @@ int halo_setup(gkob200_dist_matrix* m)
     if (!row_list.empty())
         GKOB200_CUDA(cudaMemcpy(row_list.data(), m->non_local.row_list, row_list.size() * sizeof(int32_t),
                                 cudaMemcpyDeviceToHost));
-    std::vector<int32_t> order, boundary, thread_row;
+    std::vector<int32_t> order, boundary, nl_ptrs(row_list.size() + 1, 0);
+    std::vector<int2> thread_range;
+    if (!row_list.empty())
+        GKOB200_CUDA(cudaMemcpy(nl_ptrs.data(), m->non_local.row_ptrs, nl_ptrs.size() * sizeof(int32_t),
+                                cudaMemcpyDeviceToHost));
     std::vector<char> is_boundary(static_cast<size_t>(n_blocks), 0);
     for (size_t j = 0; j < row_list.size(); ++j) {
         const int32_t blk = row_list[j] / 128;
         if (blk < 0 || blk >= n_blocks || (j > 0 && row_list[j] <= row_list[j - 1])) return GKOB200_EINVAL;
         if (boundary.empty() || boundary.back() != blk) {
             boundary.push_back(blk);
-            thread_row.resize(boundary.size() * 128, -1);
+            thread_range.resize(boundary.size() * 128, make_int2(0, 0));
             is_boundary[blk] = 1;
         }
-        thread_row[(boundary.size() - 1) * 128 + static_cast<size_t>(row_list[j] % 128)] = static_cast<int32_t>(j);
+        thread_range[(boundary.size() - 1) * 128 + static_cast<size_t>(row_list[j] % 128)] =
+            make_int2(nl_ptrs[j], nl_ptrs[j + 1]);
     }
     order.reserve(static_cast<size_t>(n_blocks));
     for (int64_t b = 0; b < n_blocks; ++b)
@@ -365,13 +379,13 @@ int halo_setup(gkob200_dist_matrix* m)
     }
     order.insert(order.end(), boundary.begin(), boundary.end());
     if ((rc = m->order.alloc(order.size() * sizeof(int32_t) + 16))) return rc;
-    if ((rc = m->nl_thread_row.alloc(thread_row.size() * sizeof(int32_t) + 16))) return rc;
+    if ((rc = m->nl_thread_range.alloc(thread_range.size() * sizeof(int2) + 16))) return rc;
     GKOB200_CUDA(cudaMemcpy(m->order.p, order.data(), order.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-    if (!thread_row.empty())
-        GKOB200_CUDA(cudaMemcpy(m->nl_thread_row.p, thread_row.data(), thread_row.size() * sizeof(int32_t),
+    if (!thread_range.empty())
+        GKOB200_CUDA(cudaMemcpy(m->nl_thread_range.p, thread_range.data(), thread_range.size() * sizeof(int2),
                                 cudaMemcpyHostToDevice));
     H.order = m->order.as<int32_t>();
-    H.nl_thread_row = m->nl_thread_row.as<int32_t>();
+    H.nl_thread_range = m->nl_thread_range.as<int2>();
     H.nl_row_ptrs = static_cast<const int32_t*>(m->non_local.row_ptrs);
     H.nl_cols = static_cast<const int32_t*>(m->non_local.col_idxs);
     H.nl_vals = m->non_local.values;
@@ -424,7 +438,7 @@ int dist_apply(gkob200_dist_matrix* m, cudaStream_t s, const V* b, int64_t bs, i
         // ---- fused path: one launch (+ the deferred-reduction finish when a dot is attached)
         SpmvFusion<V> fu;
         if (fusion) fu = *fusion;
-        if (!epoch_bumped) {
+        if (!epoch_bumped && !(dist_debug() & 1)) {
             halo_epoch_bump<<<1, 1, 0, s>>>(m->window, fu.skip);
             GKOB200_CHECK_LAUNCH();
             ++m->launches;
@@ -684,13 +698,15 @@ struct DistCgSolver : SolverBase<V> {
         P.ws = bigws.p;
         P.p2p = (dm->comm && dm->comm->p2p) ? dm->comm->p2p_dev_ptr : nullptr;
         P.halo_epoch = dm->fused ? reinterpret_cast<unsigned long long*>(dm->window + kHaloEpochOff) : nullptr;
+        if (dist_debug() & 1) P.halo_epoch = nullptr;
+        if (dist_debug() & 2) P.p2p = nullptr;
         return P;
     }
 
     int allreduce(cudaStream_t s, V* buf, size_t count)
     {
         gkob200_dist_comm* c = dm->comm;
-        if (!c || c->size == 1) return 0;
+        if (!c || c->size == 1 || (dist_debug() & 2)) return 0;
         ++launch_count;
         return comm_allreduce<V>(c, s, buf, count, &this->st()->stopped, &this->st()->stopped);
     }
@@ -738,10 +754,11 @@ struct DistCgSolver : SolverBase<V> {
             fu.p2p_buf = P.sc + D_BETA;
             fu.p2p_count = dm->fused ? 1 : 2;
         }
+        const bool no_allreduce = (dist_debug() & 2) != 0;
         int rc;
         if ((rc = dist_apply<V>(dm, s, P.p, 1, 1, nullptr, nullptr, P.q, 1, &fu, dm->fused))) return rc;
         // (a rank whose last SpMV could not exchange all-reduces with the stand-alone kernel)
-        if (!dm->exchanged && (rc = allreduce(s, P.sc + D_BETA, dm->fused ? 1 : 2))) return rc;
+        if (!dm->exchanged && !no_allreduce && (rc = allreduce(s, P.sc + D_BETA, dm->fused ? 1 : 2))) return rc;
         return update<false>(s, x);
     }
 

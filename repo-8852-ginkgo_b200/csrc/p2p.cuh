@@ -25,6 +25,8 @@
 #pragma once
 #include <cstdint>
 
+#include <cuda_runtime.h>
+
 namespace gkob200 {
 
 constexpr int kP2pMaxRanks = 16;
@@ -164,8 +166,8 @@ struct HaloDev {
     long long recv_stride;                    // values between my two receive buffers
     // ---- non-local block (row-compressed) and the CTA order ----
     const int* order;                         // slot -> row block; boundary blocks last
-    const int* nl_thread_row;                 // boundary slot j, thread t: index of row (block*128 + t) in the
-                                              // row-compressed non-local block, or -1  [128 per slot]
+    const int2* nl_thread_range;              // boundary slot j, thread t: entry range [x, y) of row
+                                              // (block*128 + t) in the non-local block  [128 per slot]
     const int* nl_row_ptrs;
     const int* nl_cols;
     const void* nl_vals;
