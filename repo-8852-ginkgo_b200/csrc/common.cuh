@@ -206,6 +206,25 @@ __device__ __forceinline__ void store_block_partial(T v, T* partials)
     const T s = block_sum(v, red_p);
     if (threadIdx.x == 0) partials[blockIdx.x] = s;
 }
+// Same, one partial per WARP and no barrier at all (the row-block SpMV on short rows: its CTAs
+// live ~3 us, two __syncthreads per CTA were 8 % of that).  Warp w of CTA b owns slot
+// b * warps + w; a second reduction uses the array right behind (gridDim.x * warps entries).
+template <typename T>
+__device__ __forceinline__ void store_warp_partial(T v, T* partials, int warps_per_cta)
+{
+    const T s = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) partials[static_cast<size_t>(blockIdx.x) * warps_per_cta + (threadIdx.x >> 5)] = s;
+}
+template <typename T>
+__device__ __forceinline__ void store_warp_partial2(T v0, T v1, T* partials, int warps_per_cta)
+{
+    const T s0 = warp_sum(v0), s1 = warp_sum(v1);
+    if ((threadIdx.x & 31) == 0) {
+        const size_t slot = static_cast<size_t>(blockIdx.x) * warps_per_cta + (threadIdx.x >> 5);
+        partials[slot] = s0;
+        partials[static_cast<size_t>(gridDim.x) * warps_per_cta + slot] = s1;
+    }
+}
 // two reductions per CTA: the second array follows the first (gridDim.x entries each)
 template <typename T>
 __device__ __forceinline__ void store_block_partial2(T v0, T v1, T* partials)

@@ -214,10 +214,11 @@ __global__ void __launch_bounds__(kRowsPerCta, rowblock_min_ctas(kBatch, sizeof(
         const int n_push = fu.halo_push_ctas;
         if (static_cast<int>(blockIdx.x) < n_push) {
             if (fu.skip && *fu.skip) return;   // no rank pushes after the stop (the flag is global)
-            halo_push_cta<V>(fu.halo, b, b_stride, fu.on_fail);
-            if (Fused && fu.out && tid == 0) {   // the deferred reduction reads one partial per CTA
-                ws_partials<V>(fu.ws)[blockIdx.x] = V(0);
-                if (fu.out_sq) ws_partials<V>(fu.ws)[gridDim.x + blockIdx.x] = V(0);
+            if (!(fu.halo_debug & 4)) halo_push_cta<V>(fu.halo, b, b_stride, fu.on_fail);
+            if (Fused && fu.out && tid < kRowsPerCta / 32) {   // the deferred reduction reads every slot
+                constexpr int W = kRowsPerCta / 32;
+                ws_partials<V>(fu.ws)[blockIdx.x * W + tid] = V(0);
+                if (fu.out_sq) ws_partials<V>(fu.ws)[(gridDim.x + blockIdx.x) * W + tid] = V(0);
             }
             return;
         }
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(kRowsPerCta, rowblock_min_ctas(kBatch, sizeof(
         // arithmetic on kernel parameters: nothing is loaded in front of the bulk copy.
         const int slot = static_cast<int>(blockIdx.x) - n_push;
         if (slot >= fu.halo_n_interior) {
-            nl_slot = slot - fu.halo_n_interior;
+            if (!(fu.halo_debug & 8)) nl_slot = slot - fu.halo_n_interior;
             blk = fu.halo->order[slot];
         } else if (fu.halo_runs > 0) {
             int r = 0;
@@ -241,8 +242,6 @@ __global__ void __launch_bounds__(kRowsPerCta, rowblock_min_ctas(kBatch, sizeof(
     const int64_t row0 = blk * kRowsPerCta;
     const int nrow = static_cast<int>(min(static_cast<int64_t>(kRowsPerCta), n_rows - row0));
     if (tid == 0) mbar_init(&bar, 1);
-    int nl_k0 = 0, nl_k1 = 0;   // boundary CTA: this thread's entries of the non-local block
-    unsigned long long halo_epoch = 0;
     // Independent loads issued back to back so that their latencies overlap: the solver's
     // "stopped" flag, this thread's two row pointers (coalesced, overlapping by one) and —
     // for the fused dot — w[row], which is only needed in the epilogue.
@@ -296,14 +295,11 @@ __global__ void __launch_bounds__(kRowsPerCta, rowblock_min_ctas(kBatch, sizeof(
             if (tid >= 32 && tid < 32 + IA && ct + (tid - 32) < chunk_end)
                 s_col[ct + (tid - 32) - cb] = col_idxs[ct + (tid - 32)];
         }
-        if (Halo && nl_slot >= 0 && chunk == tile_begin) {
-            // Boundary CTA: what the non-local tail needs is requested while the bulk copy of
-            // the local tile is in flight (one coalesced load per thread)
-            const HaloDev* __restrict__ H = fu.halo;
-            const int2 range = H->nl_thread_range[nl_slot * kRowsPerCta + tid];
-            nl_k0 = range.x;
-            nl_k1 = range.y;
-            halo_epoch = *reinterpret_cast<const unsigned long long*>(H->window + kHaloEpochOff);
+        if (Halo && nl_slot >= 0 && chunk == tile_begin && (tid & 15) == 0) {
+            // Boundary CTA: the per-thread entry ranges of the non-local tail are pulled into L2
+            // while the bulk copy of the local tile is in flight (no register lives across the
+            // row walk: the tail's first load then is an L2 hit)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(fu.halo->nl_thread_range + nl_slot * kRowsPerCta + tid));
         }
         mbar_wait(&bar, parity);
         parity ^= 1u;
@@ -340,6 +336,9 @@ __global__ void __launch_bounds__(kRowsPerCta, rowblock_min_ctas(kBatch, sizeof(
         unsigned char* win = H->window;
         __shared__ int s_wait_fail;
         if (tid == 0) s_wait_fail = 0;
+        const int2 nl_range = H->nl_thread_range[nl_slot * kRowsPerCta + tid];
+        const int nl_k0 = nl_range.x, nl_k1 = nl_range.y;
+        const unsigned long long halo_epoch = *reinterpret_cast<const unsigned long long*>(win + kHaloEpochOff);
         __syncthreads();
         if (tid < H->n_recv_peers) {
             // (acquire even when the peek already saw the flag: the entries are read next)
@@ -364,11 +363,12 @@ __global__ void __launch_bounds__(kRowsPerCta, rowblock_min_ctas(kBatch, sizeof(
     }
     if (tid < nrow) c[(row0 + tid) * c_stride] = acc;
     if (Fused && fu.out) {
-        // one partial per CTA, summed by finish_partials right after this launch
+        // one partial per warp (no barrier), summed by finish_partials right after this launch
         if (fu.out_sq)
-            store_block_partial2(tid < nrow ? acc * w_row : V(0), tid < nrow ? acc * acc : V(0), ws_partials<V>(fu.ws));
+            store_warp_partial2(tid < nrow ? acc * w_row : V(0), tid < nrow ? acc * acc : V(0), ws_partials<V>(fu.ws),
+                                kRowsPerCta / 32);
         else
-            store_block_partial(tid < nrow ? acc * w_row : V(0), ws_partials<V>(fu.ws));
+            store_warp_partial(tid < nrow ? acc * w_row : V(0), ws_partials<V>(fu.ws), kRowsPerCta / 32);
     }
 }
 
@@ -714,8 +714,9 @@ int csr_spmv_launch(cudaStream_t s, int64_t n_rows, int64_t n_cols, int64_t nnz,
         if (halo && !(aligned && rowblock_variant() == 1 && sizeof(I) == 4)) return GKOB200_EUNSUPPORTED;
         if (aligned && rowblock_variant() == 1) {
             // the deferred reduction leaves one partial per CTA (and array) in fu.ws
+            constexpr int kWarps = kRowsPerCta / 32;
             if (fused && fu.out &&
-                static_cast<int64_t>(grid) * (fu.out_sq ? 2 : 1) + 2 * kFinishMaxCtas >
+                static_cast<int64_t>(grid) * kWarps * (fu.out_sq ? 2 : 1) + 2 * kFinishMaxCtas >
                     (fu.ws_blocks + 256) * kReduceMaxVals)
                 return GKOB200_EWORKSPACE;
             // stream-ahead distance: one wave of resident CTAs (shared-memory or thread bound)
@@ -751,7 +752,7 @@ int csr_spmv_launch(cudaStream_t s, int64_t n_rows, int64_t n_cols, int64_t nnz,
 #undef GKOB200_RBT_B
 #undef GKOB200_RBT
             GKOB200_CHECK_LAUNCH();
-            if (fused && fu.out) return launch_finish_partials<V>(s, static_cast<int64_t>(grid), fu);
+            if (fused && fu.out) return launch_finish_partials<V>(s, static_cast<int64_t>(grid) * kWarps, fu);
             return 0;
         }
         if (fused && fu.out && static_cast<int64_t>(grid) * (fu.out_sq ? 2 : 1) > fu.ws_blocks) return GKOB200_EWORKSPACE;

@@ -237,6 +237,7 @@ int comm_allreduce(gkob200_dist_comm* c, cudaStream_t s, V* buf, size_t count, c
 // Measurement-only switches (tools/dist_ab.py; results are WRONG with any bit set):
 //   bit 0: do not enter a new halo epoch (no rank ever waits for a neighbour)
 //   bit 1: skip the scalar all-reduces of the distributed CG
+//   bit 2: the push CTAs of the fused SpMV do nothing       bit 3: no non-local tail
 inline int dist_debug()
 {
     const char* e = getenv("GKOB200_DIST_DEBUG");
@@ -446,6 +447,7 @@ int dist_apply(gkob200_dist_matrix* m, cudaStream_t s, const V* b, int64_t bs, i
         fu.halo = m->halo_dev.as<HaloDev>();
         fu.halo_push_ctas = m->n_push;
         fu.halo_n_interior = m->n_interior;
+        fu.halo_debug = dist_debug();
         fu.halo_runs = m->n_runs;
         for (int i = 0; i < kHaloRuns; ++i) {
             fu.halo_run_slot[i] = m->run_slot[i];

@@ -33,6 +33,7 @@ struct SpmvFusion {
     // held in the kernel parameters (no dependent load in front of the bulk copy): run i covers
     // slots [halo_run_slot[i], halo_run_slot[i+1]) -> blocks halo_run_block[i] + (slot - ...).
     // halo_runs == 0: look the slot up in halo->order (scattered boundary rows).
+    int halo_debug = 0;      // measurement only (GKOB200_DIST_DEBUG): 4 = push CTAs idle, 8 = no non-local tail
     int halo_n_interior = 0;
     int halo_runs = 0;
     int halo_run_slot[kHaloRuns + 1] = {};

@@ -50,9 +50,12 @@ def main():
 
     out = {"world": world, "rows_per_gpu": n, "fused": A.uses_fused_halo}
     out["spmv_local_alone_us"] = timed(lambda: A.local.apply(p, q), 50)
-    for dbg, name in ((0, "spmv_dist_us"), (1, "spmv_dist_no_epoch_us")):
-        os.environ["GKOB200_DIST_DEBUG"] = str(dbg)
-        out[name] = timed(lambda: A.apply(p, q), 50)
+    for rep in range(3):
+        for dbg, name in ((0, "spmv_dist_us"), (1, "spmv_dist_no_epoch_us"), (1 + 4, "spmv_dist_no_epoch_no_push_us"),
+                          (1 + 8, "spmv_dist_no_epoch_no_tail_us"), (1 + 4 + 8, "spmv_dist_no_epoch_no_push_no_tail_us")):
+            os.environ["GKOB200_DIST_DEBUG"] = str(dbg)
+            out.setdefault(name, []).append(round(timed(lambda: A.apply(p, q), 50), 1))
+        out.setdefault("spmv_local_alone_again_us", []).append(round(timed(lambda: A.local.apply(p, q), 50), 1))
     s_loc = gko.solver.Cg.build().with_criteria(gko.stop.Iteration(iters)).with_check_every(iters).on(exec_).generate(A.local)
 
     def loc():
