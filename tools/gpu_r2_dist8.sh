@@ -21,4 +21,3 @@ echo "== weak N=4, N=2"; run_bench 4 r2_weak_n4; run_bench 2 r2_weak_n2
 echo "== strong N=4, N=2"; run_bench 4 r2_strong_n4 --scaling strong --no-verify; run_bench 2 r2_strong_n2 --scaling strong --no-verify
 echo "== weak N=8 fallback paths"
 GKOB200_FUSED_HALO=0 run_bench 8 r2_weak_n8_nofuse --no-verify
-GKOB200_P2P=0 run_bench 8 r2_weak_n8_nccl --no-verify
