@@ -439,6 +439,17 @@ GKOB200_DECL_SETUP(f64, double, i32, int32_t)
 GKOB200_DECL_SETUP(f32, float, i32, int32_t)
 GKOB200_DECL_SETUP(f64, double, i64, int64_t)
 GKOB200_DECL_SETUP(f32, float, i64, int64_t)
+/* device_matrix_data <-> array<matrix_data_entry> [ref: components::aos_to_soa / soa_to_aos,
+ * core/base/device_matrix_data_kernels.hpp:54-62; reference/base/device_matrix_data_kernels.cpp:50-80].
+ * `entries`: nnz structs { I row; I column; V value; } with natural alignment, device memory. */
+#define GKOB200_DECL_AOS(V, VT, I, IT)                                                                             \
+    int gkob200_aos_to_soa_##V##_##I(void* stream, int64_t nnz, const void* entries, IT* rows, IT* cols, VT* vals); \
+    int gkob200_soa_to_aos_##V##_##I(void* stream, int64_t nnz, const IT* rows, const IT* cols, const VT* vals,    \
+                                     void* entries);
+GKOB200_DECL_AOS(f64, double, i32, int32_t)
+GKOB200_DECL_AOS(f32, float, i32, int32_t)
+GKOB200_DECL_AOS(f64, double, i64, int64_t)
+GKOB200_DECL_AOS(f32, float, i64, int64_t)
 
 /* ------------------------------------------------------------------------- *
  * Wire / disk formats of the callers (host code, no GPU needed)

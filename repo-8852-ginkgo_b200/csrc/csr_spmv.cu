@@ -373,18 +373,11 @@ __global__ void __launch_bounds__(kRowsPerCta, rowblock_min_ctas(kBatch, sizeof(
 }
 
 // ---------------------------------------------------------------------------
-// merge-path kernel (single right-hand side), one tile per WARP
+// merge-path kernel (single right-hand side)
 // ---------------------------------------------------------------------------
-// Round 1 ran one tile of 2304 merge items per CTA with six __syncthreads between its phases;
-// ncu showed no unit above 41 % and the stalls split between barrier / scoreboard waits: the
-// phases of a CTA serialise and only six CTAs fit an SM.  Here a WARP owns a tile of 288 merge
-// items (9 per lane: an odd stride keeps the transposed shared-memory reads conflict-free) and
-// never meets a CTA-wide barrier: 48 independent warps per SM overlap their stream loads,
-// gathers and reductions freely, and the instruction count per entry drops threefold.
-constexpr int kMpThreads = 128;                        // 4 independent warps per CTA
-constexpr int kMpWarps = kMpThreads / 32;
-constexpr int kMpItems = 9;                            // merge items per lane (odd: conflict-free)
-constexpr int kMpTile = 32 * kMpItems;                 // merge items per warp tile
+constexpr int kMpThreads = 256;
+constexpr int kMpItems = 9;                            // merge items per thread (odd: conflict-free)
+constexpr int kMpTile = kMpThreads * kMpItems;         // merge items per CTA
 
 // Merge-path diagonal search: how many of the first `diag` merge items are row
 // ends.  List A = row end offsets row_ptrs[1..n], list B = 0..nnz-1; a row end is
@@ -406,113 +399,106 @@ __device__ __forceinline__ int64_t merge_path_search(int64_t diag, const P row_e
 }
 
 template <typename V, typename I, bool Advanced>
-__global__ void __launch_bounds__(kMpThreads, 10)
+__global__ void __launch_bounds__(kMpThreads)
     csr_spmv_merge(int64_t n_rows, int64_t nnz, const I* __restrict__ row_ptrs, const I* __restrict__ col_idxs,
                    const V* __restrict__ values, const V* __restrict__ b, int64_t b_stride,
                    const V* __restrict__ alpha_p, const V* __restrict__ beta_p, V* __restrict__ c,
                    int64_t c_stride, int64_t* __restrict__ carry_row, V* __restrict__ carry_val,
-                   const int64_t* __restrict__ plan, float keep_frac, int64_t n_tiles)
+                   const int64_t* __restrict__ plan, float keep_frac)
 {
     // The merge path only cuts the matrix into tiles of equal rows + entries; inside a tile
     // the row sums are a segmented reduction over the tile's products:
-    //   s_prod[k]  product of entry k (coalesced loads, gathers batched per lane)
+    //   s_prod[k]  product of entry k (coalesced loads, gathers batched per thread)
     //   s_head[k]  tile row that STARTS at entry k, or -1
-    // lane l owns the kMpItems consecutive entries [l*kMpItems, ...): it reads them and their
-    // heads back with independent shared-memory reads and reduces them in registers; rows that
-    // span lanes are stitched in lane order (left-to-right association).
-    __shared__ V s_prod_all[kMpWarps][kMpTile];
-    __shared__ short s_head_all[kMpWarps][kMpTile];
-    __shared__ V s_lead_all[kMpWarps][32];      // sum of a lane's entries before its first head
-    __shared__ short s_last_all[kMpWarps][32];  // tile row of its last head, -1: no head in the window
+    // thread t owns the kMpItems consecutive entries [t*kMpItems, ...): it loads them and their
+    // heads with independent shared-memory reads and reduces them in registers (no search, no
+    // dependent shared-memory chain); rows that span threads are stitched in thread order.
+    __shared__ V s_prod[kMpTile];
+    __shared__ int s_head[kMpTile];
+    __shared__ int64_t s_range[4];
+    __shared__ V s_lead[kMpThreads];      // sum of a thread's entries before its first head
+    __shared__ V s_trail[kMpThreads];     // sum of its entries from its last head on
+    __shared__ int s_last[kMpThreads];    // tile row of its last head, -1: no head in the window
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t tile = static_cast<int64_t>(blockIdx.x) * kMpWarps + warp;
-    if (tile >= n_tiles) return;   // (whole warps leave; nothing below is a CTA-wide barrier)
-    V* s_prod = s_prod_all[warp];
-    short* s_head = s_head_all[warp];
-    V* s_lead = s_lead_all[warp];
-    short* s_last = s_last_all[warp];
-
+    const int tid = threadIdx.x;
     const int64_t total = n_rows + nnz;
-    const int64_t diag0 = min(tile * kMpTile, total);
+    const int64_t diag0 = min(static_cast<int64_t>(blockIdx.x) * kMpTile, total);
     const int64_t diag1 = min(diag0 + kMpTile, total);
     const I* row_end = row_ptrs + 1;
-    int64_t split = 0;
-    if (lane < 2) {
-        const int64_t d = lane == 0 ? diag0 : diag1;
+    if (tid < 2) {
+        const int64_t d = tid == 0 ? diag0 : diag1;
         // planned: the tile's split point was computed once per matrix (gkob200_csr_merge_plan_*),
-        // otherwise two binary searches over row_ptrs per tile and per call
-        split = plan ? plan[tile + lane] : merge_path_search<I>(d, row_end, n_rows, nnz);
+        // otherwise two binary searches over row_ptrs per CTA and per call (24 dependent loads
+        // at 10^7 rows)
+        const int64_t r = plan ? plan[blockIdx.x + tid] : merge_path_search<I>(d, row_end, n_rows, nnz);
+        s_range[tid * 2] = r;
+        s_range[tid * 2 + 1] = d - r;
     }
-    const int64_t r_begin = __shfl_sync(0xffffffffu, split, 0), r_end = __shfl_sync(0xffffffffu, split, 1);
-    const int64_t k_begin = diag0 - r_begin, k_end = diag1 - r_end;
+#pragma unroll
+    for (int u = 0; u < kMpItems; ++u) s_head[tid + u * kMpThreads] = -1;
+    __syncthreads();
+    const int64_t r_begin = s_range[0], k_begin = s_range[1];
+    const int64_t r_end = s_range[2], k_end = s_range[3];
     const int n_tile_rows = static_cast<int>(r_end - r_begin);   // rows that END in this tile
     const int n_tile_nnz = static_cast<int>(k_end - k_begin);
     V alpha = V(1);
     if (Advanced) alpha = *alpha_p;
 
-    // coalesced staging of the products.  Every lane first issues all its (col, val) loads,
-    // then all its gathers, then forms the products: kMpItems independent requests in flight per
-    // lane (the gathers of a skewed matrix are random 32-byte sectors — latency, not bandwidth,
-    // is what has to be hidden).  Streams are marked evict_first, the gathered vector
-    // evict_last (see tma.cuh).
+    // coalesced staging of the products.  Every thread first issues all its (col, val) loads,
+    // then all its gathers, then forms the products: up to kMpItems independent requests in
+    // flight per thread (the gathers of a skewed matrix are random 32-byte sectors — latency,
+    // not bandwidth, is what has to be hidden).  Streams are marked evict_first, the gathered
+    // vector evict_last (see tma.cuh).
     {
         const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last(keep_frac);
         V v[kMpItems], xv[kMpItems];
         I col[kMpItems];
 #pragma unroll
         for (int u = 0; u < kMpItems; ++u) {
-            const int k = lane + u * 32;
-            col[u] = k < n_tile_nnz ? ld_hint(col_idxs + k_begin + k, pol_stream) : I(0);
-            s_head[k] = -1;
+            const int k = tid + u * kMpThreads;
+            const bool in = k < n_tile_nnz;
+            col[u] = in ? ld_hint(col_idxs + k_begin + k, pol_stream) : I(0);
+            v[u] = in ? ld_hint(values + k_begin + k, pol_stream) : V(0);
         }
-        // (gathers before the value loads: the column registers die here, so the 9 values and
-        // the 9 gathered entries are the only batches alive together)
 #pragma unroll
         for (int u = 0; u < kMpItems; ++u) xv[u] = ld_hint(b + static_cast<int64_t>(col[u]) * b_stride, pol_keep);
-#pragma unroll
-        for (int u = 0; u < kMpItems; ++u) {
-            const int k = lane + u * 32;
-            v[u] = k < n_tile_nnz ? ld_hint(values + k_begin + k, pol_stream) : V(0);
-        }
-        __syncwarp();   // s_head cleared before the heads are marked
         // heads: tile row r (1 <= r <= n_tile_rows; r == n_tile_rows is the row left open at the
         // end of the tile) starts where row r-1 ends, if it has an entry in this tile.  Tile
         // row 0 is open when the tile starts (its head, if any, lies in an earlier tile).
-        for (int r = lane + 1; r <= n_tile_rows; r += 32) {
+        for (int r = tid + 1; r <= n_tile_rows; r += kMpThreads) {
             const int start = static_cast<int>(static_cast<int64_t>(row_end[r_begin + r - 1]) - k_begin);
             const int end = r < n_tile_rows ? static_cast<int>(static_cast<int64_t>(row_end[r_begin + r]) - k_begin)
                                             : n_tile_nnz;
-            if (start < end) s_head[start] = static_cast<short>(r);
+            if (start < end) s_head[start] = r;
         }
 #pragma unroll
         for (int u = 0; u < kMpItems; ++u) {
-            const int k = lane + u * 32;
+            const int k = tid + u * kMpThreads;
             // entries past the end of the tile count as zeros of the open row
             s_prod[k] = k < n_tile_nnz ? (Advanced ? mul_rn(mul_rn(alpha, v[u]), xv[u]) : mul_rn(v[u], xv[u])) : V(0);
         }
     }
-    __syncwarp();
+    __syncthreads();
 
-    // per-lane segmented reduction in registers
+    // per-thread segmented reduction in registers
     V p[kMpItems];
     int h[kMpItems];
 #pragma unroll
     for (int u = 0; u < kMpItems; ++u) {
-        p[u] = s_prod[lane * kMpItems + u];
-        h[u] = s_head[lane * kMpItems + u];
+        p[u] = s_prod[tid * kMpItems + u];
+        h[u] = s_head[tid * kMpItems + u];
     }
-    __syncwarp();   // s_prod is reused for the row results from here on
+    __syncthreads();   // s_prod is reused for the row results from here on
     V* s_out = s_prod;
-    for (int r = lane; r < n_tile_rows; r += 32) s_out[r] = V(0);   // empty rows, and rows stitched below
-    __syncwarp();
+    for (int r = tid; r < n_tile_rows; r += kMpThreads) s_out[r] = V(0);   // empty rows, and rows stitched below
+    __syncthreads();
     V lead = V(0), acc = V(0);
     int cur = -1;   // tile row being accumulated; -1: the row open at the start of the window
 #pragma unroll
     for (int u = 0; u < kMpItems; ++u) {
         if (h[u] >= 0) {
             // a row starts here: what was accumulated so far is complete for `cur` unless cur
-            // is the window's leading segment (that one is stitched with earlier lanes)
+            // is the window's leading segment (that one is stitched with earlier threads)
             if (cur < 0)
                 lead = acc;
             else
@@ -527,22 +513,23 @@ __global__ void __launch_bounds__(kMpThreads, 10)
         lead = acc;
         acc = V(0);
     }
-    s_lead[lane] = lead;
-    s_last[lane] = static_cast<short>(cur);
-    if (lane == 0) {
+    s_lead[tid] = lead;
+    s_trail[tid] = acc;
+    s_last[tid] = cur;
+    if (tid == 0) {
         // default: no carry (the open row has no entry in this tile yet); overwritten below
-        carry_row[tile] = -1;
-        carry_val[tile] = V(0);
+        carry_row[blockIdx.x] = -1;
+        carry_val[blockIdx.x] = V(0);
     }
-    __syncwarp();
-    // Stitch in lane order (left-to-right association).  The lane holding the last head of a
-    // row adds its trailing sum and the leading sums of the following lanes up to and including
-    // the next lane that has a head; lane 0 does the same for the row that was open when the
-    // tile started.
+    __syncthreads();
+    // Stitch in thread order (left-to-right association).  The thread holding the last head of
+    // a row adds its trailing sum and the leading sums of the following threads up to and
+    // including the next thread that has a head; thread 0 does the same for the row that was
+    // open when the tile started.
     {
         auto run_from = [&](V run, int t) {
-            // add lead[t], lead[t+1], ... until (and including) the first lane with a head
-            while (t < 32) {
+            // add lead[t], lead[t+1], ... until (and including) the first thread with a head
+            while (t < kMpThreads) {
                 run = add_rn(run, s_lead[t]);
                 if (s_last[t] >= 0) break;
                 ++t;
@@ -553,16 +540,16 @@ __global__ void __launch_bounds__(kMpThreads, 10)
             if (row < n_tile_rows) {
                 s_out[row] = run;
             } else {
-                // the row continues into the next tile: per-tile carry
-                carry_row[tile] = r_begin + row;
-                carry_val[tile] = run;
+                // the row continues into the next tile: per-CTA carry
+                carry_row[blockIdx.x] = r_begin + row;
+                carry_val[blockIdx.x] = run;
             }
         };
-        if (lane == 0) deliver(0, run_from(V(0), 0));
-        if (cur >= 0) deliver(cur, run_from(acc, lane + 1));
+        if (tid == 0) deliver(0, run_from(V(0), 0));
+        if (cur >= 0) deliver(cur, run_from(acc, tid + 1));
     }
-    __syncwarp();
-    for (int r = lane; r < n_tile_rows; r += 32) {
+    __syncthreads();
+    for (int r = tid; r < n_tile_rows; r += kMpThreads) {
         const int64_t row = r_begin + r;
         // beta*c is applied exactly once, by the tile in which the row ends
         c[row * c_stride] = Advanced ? add_rn(mul_rn(c[row * c_stride], *beta_p), s_out[r]) : s_out[r];
@@ -675,61 +662,6 @@ inline int rowblock_prefetch()
     static int v = env_int("GKOB200_CSR_PREFETCH", -1);  // -1: one resident wave
     return v;
 }
-
-// The gathered vector of a skewed matrix is read at random (one 32-byte sector per entry): the
-// kernel is only fast if it stays in L2 while 1.2 GB of matrix streams pass through.  For the
-// duration of the merge-path launch the stream carries an access-policy window over b marked
-// persisting (as much of it as the device's persisting-L2 carve-out holds, the rest streaming);
-// the carve-out is configured once per device.  GKOB200_L2_PERSIST=0 disables it.
-struct L2PersistWindow {
-    cudaStream_t s;
-    bool active = false;
-    L2PersistWindow(cudaStream_t stream, const void* ptr, size_t bytes) : s(stream)
-    {
-        static const int enabled = [] {
-            const char* e = getenv("GKOB200_L2_PERSIST");
-            return (e && e[0] == '0') ? 0 : 1;
-        }();
-        if (!enabled || !ptr || bytes < (size_t(8) << 20)) return;   // small vectors stay resident anyway
-        struct DevCfg { size_t carve = 0, window = 0; bool done = false; };
-        static DevCfg cfg[64];
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
-        DevCfg& d = cfg[dev];
-        if (!d.done) {
-            d.done = true;
-            int max_persist = 0, max_window = 0;
-            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
-            cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-            if (max_persist > 0 && max_window > 0 &&
-                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, static_cast<size_t>(max_persist)) == cudaSuccess) {
-                d.carve = static_cast<size_t>(max_persist);
-                d.window = static_cast<size_t>(max_window);
-            }
-            cudaGetLastError();
-        }
-        if (d.carve == 0) return;
-        cudaStreamAttrValue attr{};
-        attr.accessPolicyWindow.base_ptr = const_cast<void*>(ptr);
-        attr.accessPolicyWindow.num_bytes = bytes < d.window ? bytes : d.window;
-        const double ratio = static_cast<double>(d.carve) * 0.95 / static_cast<double>(attr.accessPolicyWindow.num_bytes);
-        attr.accessPolicyWindow.hitRatio = ratio >= 1.0 ? 1.0f : static_cast<float>(ratio);
-        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        active = cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
-        cudaGetLastError();
-    }
-    void release()
-    {
-        if (!active) return;
-        cudaStreamAttrValue attr{};
-        attr.accessPolicyWindow.num_bytes = 0;
-        cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr);
-        cudaGetLastError();
-        active = false;
-    }
-    ~L2PersistWindow() { release(); }
-};
 
 inline int rowblock_cap(int64_t max_block_nnz, size_t elem_bytes)
 {
@@ -851,17 +783,14 @@ int csr_spmv_launch(cudaStream_t s, int64_t n_rows, int64_t n_cols, int64_t nnz,
         const char* f = getenv("GKOB200_MP_KEEP_FRAC");
         return f ? static_cast<float>(atof(f)) : 1.0f;
     }();
-    const unsigned mp_grid = static_cast<unsigned>(ceildiv(n_tiles, kMpWarps));
-    L2PersistWindow keep(s, b, static_cast<size_t>(n_cols) * static_cast<size_t>(b_stride) * sizeof(V));
     if (adv)
-        csr_spmv_merge<V, I, true><<<mp_grid, kMpThreads, 0, s>>>(n_rows, nnz, row_ptrs, col_idxs, values, b, b_stride,
-                                                                   alpha, beta, c, c_stride, carry_row, carry_val, plan,
-                                                                   keep_frac, n_tiles);
+        csr_spmv_merge<V, I, true><<<static_cast<unsigned>(n_tiles), kMpThreads, 0, s>>>(
+            n_rows, nnz, row_ptrs, col_idxs, values, b, b_stride, alpha, beta, c, c_stride, carry_row,
+            carry_val, plan, keep_frac);
     else
-        csr_spmv_merge<V, I, false><<<mp_grid, kMpThreads, 0, s>>>(n_rows, nnz, row_ptrs, col_idxs, values, b, b_stride,
-                                                                    alpha, beta, c, c_stride, carry_row, carry_val, plan,
-                                                                    keep_frac, n_tiles);
-    keep.release();
+        csr_spmv_merge<V, I, false><<<static_cast<unsigned>(n_tiles), kMpThreads, 0, s>>>(
+            n_rows, nnz, row_ptrs, col_idxs, values, b, b_stride, alpha, beta, c, c_stride, carry_row,
+            carry_val, plan, keep_frac);
     GKOB200_CHECK_LAUNCH();
     csr_spmv_merge_fixup<V><<<static_cast<unsigned>(ceildiv(n_tiles, 8)), 256, 0, s>>>(
         static_cast<int>(n_tiles), carry_row, carry_val, n_rows, c, c_stride);

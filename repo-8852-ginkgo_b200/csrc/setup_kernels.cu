@@ -336,6 +336,41 @@ int csr_sort_by_column_index(cudaStream_t s, int64_t n_rows, int64_t n_cols, int
     return 0;
 }
 
+// matrix_data_entry<V, I> of the reference: { I row; I column; V value; } with natural alignment
+// (include/ginkgo/core/base/matrix_data.hpp:89-118)
+template <typename V, typename I>
+struct Entry {
+    I row;
+    I column;
+    V value;
+};
+template <typename V, typename I>
+__global__ void __launch_bounds__(256) aos_to_soa_kernel(int64_t nnz, const Entry<V, I>* __restrict__ in, I* rows,
+                                                         I* cols, V* vals)
+{
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nnz;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const Entry<V, I> e = in[i];
+        rows[i] = e.row;
+        cols[i] = e.column;
+        vals[i] = e.value;
+    }
+}
+template <typename V, typename I>
+__global__ void __launch_bounds__(256) soa_to_aos_kernel(int64_t nnz, const I* __restrict__ rows,
+                                                         const I* __restrict__ cols, const V* __restrict__ vals,
+                                                         Entry<V, I>* out)
+{
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nnz;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        Entry<V, I> e;
+        e.row = rows[i];
+        e.column = cols[i];
+        e.value = vals[i];
+        out[i] = e;
+    }
+}
+
 }  // namespace
 }  // namespace gkob200
 
@@ -372,5 +407,31 @@ GKOB200_DEF_SETUP(f32, float, i32, int32_t)
 GKOB200_DEF_SETUP(f64, double, i64, int64_t)
 GKOB200_DEF_SETUP(f32, float, i64, int64_t)
 #undef GKOB200_DEF_SETUP
+
+#define GKOB200_DEF_AOS(V, VT, I, IT)                                                                              \
+    int gkob200_aos_to_soa_##V##_##I(void* st, int64_t nnz, const void* entries, IT* rows, IT* cols, VT* vals)     \
+    {                                                                                                              \
+        if (nnz < 0 || (nnz > 0 && (!entries || !rows || !cols || !vals))) return GKOB200_EINVAL;                  \
+        if (nnz == 0) return 0;                                                                                    \
+        aos_to_soa_kernel<VT, IT><<<grid_for(nnz, 256, 8), 256, 0, as_stream(st)>>>(                               \
+            nnz, static_cast<const Entry<VT, IT>*>(entries), rows, cols, vals);                                    \
+        GKOB200_CHECK_LAUNCH();                                                                                    \
+        return 0;                                                                                                  \
+    }                                                                                                              \
+    int gkob200_soa_to_aos_##V##_##I(void* st, int64_t nnz, const IT* rows, const IT* cols, const VT* vals,        \
+                                     void* entries)                                                                \
+    {                                                                                                              \
+        if (nnz < 0 || (nnz > 0 && (!entries || !rows || !cols || !vals))) return GKOB200_EINVAL;                  \
+        if (nnz == 0) return 0;                                                                                    \
+        soa_to_aos_kernel<VT, IT><<<grid_for(nnz, 256, 8), 256, 0, as_stream(st)>>>(                               \
+            nnz, rows, cols, vals, static_cast<Entry<VT, IT>*>(entries));                                          \
+        GKOB200_CHECK_LAUNCH();                                                                                    \
+        return 0;                                                                                                  \
+    }
+GKOB200_DEF_AOS(f64, double, i32, int32_t)
+GKOB200_DEF_AOS(f32, float, i32, int32_t)
+GKOB200_DEF_AOS(f64, double, i64, int64_t)
+GKOB200_DEF_AOS(f32, float, i64, int64_t)
+#undef GKOB200_DEF_AOS
 
 }  // extern "C"
