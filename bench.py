@@ -58,6 +58,9 @@ def parse():
     ap.add_argument("--ref-iters-per-step", type=int, default=4)
     ap.add_argument("--cpu-baseline-iters", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config-block", action="store_true",
+                    help="N=1: skip the per-config block (C1, C3, C4 slab, C5 SpMV roofline + solver iterations/s)")
+    ap.add_argument("--small-config-block", action="store_true", help="N=1: tiny sizes in the per-config block (smoke)")
     ap.add_argument("--spmv-reps", type=int, default=50)
     ap.add_argument("--format", default="csr", choices=["csr", "sellp", "ell", "hybrid", "coo"])
     return ap.parse_args()
@@ -211,8 +214,10 @@ STENCIL_DIAG_REF = {"7pt": 6.0, "27pt": 26.0}
 
 
 def ncu_traffic(fmt, grid):
-    """DRAM read + write bytes per launch of the dominant kernel, from the committed
-    `ncu --set full` capture (profiles/r01_traffic.json; written by tools/ncu_summary.py)."""
+    """DRAM read + write bytes per launch of the dominant kernel.  ncu cannot run inside a timed
+    benchmark, so this is NOT measured in this run: it is read from the committed `ncu --set full`
+    capture of the same kernel and matrix (profiles/r01_traffic.json, written by
+    tools/ncu_summary.py from profiles/r01_csr_spmv_rowblock_tma_v3_ncu_full.txt)."""
     try:
         with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
             return json.load(f).get(f"{fmt}_27pt_{grid}")
@@ -330,13 +335,20 @@ def main():
         "roofline": {"bound": "hbm", "kernel": f"{args.format}_spmv", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src, "frac_of_nominal_8000": achieved / 8000.0,
                      "bytes_per_launch": spmv_bytes, "us_per_launch": spmv_s * 1e6,
-                     "traffic": ncu_traffic(args.format, g)},
+                     "traffic": ncu_traffic(args.format, g),
+                     "traffic_source": "committed ncu --set full capture of this kernel on this matrix "
+                                       "(profiles/r01_csr_spmv_rowblock_tma_v3_ncu_full.txt), not measured in this run"},
         "cg_iteration": {"us": 1e6 * secs / (args.steps * iters), "model_bytes": it_bytes,
                          "model_gbs": it_bytes * args.steps * iters / secs / 1e9,
                          "frac_of_peak": it_bytes * args.steps * iters / secs / 1e9 / peak},
     }
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, rp, ci, va, n)
+    if not args.no_config_block:
+        del A, Aop, solver, jacobi, db, dx, p, q, rp, ci, va
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from config_block import run_block
+        line["configs"] = run_block(gko, exec_, peak, small=args.small_config_block)
     print(json.dumps(line), flush=True)
 
 

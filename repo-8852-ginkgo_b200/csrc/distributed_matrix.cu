@@ -550,8 +550,16 @@ struct DistCgParams {
     unsigned long long* halo_epoch;   // non-null: dist_cg_direction enters the next halo epoch
 };
 
+template <typename V>
+struct Pair;
+template <>
+struct Pair<double> { using type = double2; };
+template <>
+struct Pair<float> { using type = float2; };
+
 // x += t p ; r -= t q ; z = M^-1 r ; partial sums (r.z, r.r) -> sc[D_RED0..1]
-template <typename V, int Mode, bool First>
+// Wide: all vectors 16-byte aligned, n even: two rows per thread through 128-bit accesses
+template <typename V, int Mode, bool First, bool Wide>
 __global__ void __launch_bounds__(256) dist_cg_update(DistCgParams<V> P)
 {
     if (P.st->stopped) return;
@@ -564,20 +572,53 @@ __global__ void __launch_bounds__(256) dist_cg_update(DistCgParams<V> P)
     }
     V acc[2] = {V(0), V(0)};
     const int64_t step = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < P.n; i += step) {
-        V ri = P.r[i];
-        if (upd) {
-            P.x[i] = add_rn(P.x[i], mul_rn(t, P.p[i]));
-            ri = sub_rn(ri, mul_rn(t, P.q[i]));
-            P.r[i] = ri;
+    const int64_t tid0 = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (Wide) {
+        using V2 = typename Pair<V>::type;
+        V2* __restrict__ x2 = reinterpret_cast<V2*>(P.x);
+        V2* __restrict__ r2 = reinterpret_cast<V2*>(P.r);
+        V2* __restrict__ z2 = reinterpret_cast<V2*>(P.z);
+        const V2* __restrict__ p2 = reinterpret_cast<const V2*>(P.p);
+        const V2* __restrict__ q2 = reinterpret_cast<const V2*>(P.q);
+        const V2* __restrict__ d2 = reinterpret_cast<const V2*>(P.inv_diag);
+        for (int64_t i = tid0; i < P.n / 2; i += step) {
+            V2 rv = r2[i];
+            if (upd) {
+                V2 xv = x2[i];
+                const V2 pv = p2[i], qv = q2[i];
+                xv.x = add_rn(xv.x, mul_rn(t, pv.x));
+                xv.y = add_rn(xv.y, mul_rn(t, pv.y));
+                rv.x = sub_rn(rv.x, mul_rn(t, qv.x));
+                rv.y = sub_rn(rv.y, mul_rn(t, qv.y));
+                x2[i] = xv;
+                r2[i] = rv;
+            }
+            V2 zv = rv;
+            if (Mode == 1) {
+                const V2 dv = d2[i];
+                zv.x = mul_rn(rv.x, dv.x);
+                zv.y = mul_rn(rv.y, dv.y);
+                z2[i] = zv;
+            }
+            acc[0] += rv.x * zv.x + rv.y * zv.y;
+            acc[1] += rv.x * rv.x + rv.y * rv.y;
         }
-        V zi = ri;
-        if (Mode == 1) {
-            zi = mul_rn(ri, P.inv_diag[i]);
-            P.z[i] = zi;
+    } else {
+        for (int64_t i = tid0; i < P.n; i += step) {
+            V ri = P.r[i];
+            if (upd) {
+                P.x[i] = add_rn(P.x[i], mul_rn(t, P.p[i]));
+                ri = sub_rn(ri, mul_rn(t, P.q[i]));
+                P.r[i] = ri;
+            }
+            V zi = ri;
+            if (Mode == 1) {
+                zi = mul_rn(ri, P.inv_diag[i]);
+                P.z[i] = zi;
+            }
+            acc[0] += ri * zi;
+            acc[1] += ri * ri;
         }
-        acc[0] += ri * zi;
-        acc[1] += ri * ri;
     }
     DistCgParams<V> Q = P;
     grid_reduce<2>(acc, ws_partials<V>(P.ws), ws_ticket(P.ws), [Q](V(&tot)[2]) {
@@ -610,7 +651,7 @@ __global__ void dist_cg_scalars(DistCgParams<V> P)
     criterion_check(P.st, 1, P.sc + D_TAU, P.sc + D_ORIG_TAU, P.factor, P.max_iters, true, P.stop_status, P.hist, true);
 }
 
-template <typename V, bool ZisR>
+template <typename V, bool ZisR, bool Wide>
 __global__ void __launch_bounds__(256) dist_cg_direction(DistCgParams<V> P)
 {
     if (P.st->stopped) return;
@@ -620,8 +661,26 @@ __global__ void __launch_bounds__(256) dist_cg_direction(DistCgParams<V> P)
     const V t = zero_prev ? V(0) : div_rn(P.sc[D_RHO], prev);
     const V* __restrict__ z = ZisR ? P.r : P.z;
     const int64_t step = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < P.n; i += step)
-        P.p[i] = zero_prev ? z[i] : add_rn(z[i], mul_rn(t, P.p[i]));
+    const int64_t tid0 = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (Wide) {
+        using V2 = typename Pair<V>::type;
+        const V2* __restrict__ z2 = reinterpret_cast<const V2*>(z);
+        V2* __restrict__ p2 = reinterpret_cast<V2*>(P.p);
+        for (int64_t i = tid0; i < P.n / 2; i += step) {
+            const V2 zv = z2[i];
+            if (zero_prev) {
+                p2[i] = zv;
+            } else {
+                const V2 pv = p2[i];
+                V2 o;
+                o.x = add_rn(zv.x, mul_rn(t, pv.x));
+                o.y = add_rn(zv.y, mul_rn(t, pv.y));
+                p2[i] = o;
+            }
+        }
+        return;
+    }
+    for (int64_t i = tid0; i < P.n; i += step) P.p[i] = zero_prev ? z[i] : add_rn(z[i], mul_rn(t, P.p[i]));
 }
 
 template <typename V>
@@ -705,6 +764,14 @@ struct DistCgSolver : SolverBase<V> {
         return P;
     }
 
+    // 128-bit accesses: every vector on 16 bytes and an even (float: multiple of 4) row count
+    bool wide_ok(const V* x) const
+    {
+        auto al = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
+        return n >= 2 && (static_cast<size_t>(n) * sizeof(V)) % 16 == 0 && al(x) && al(vecs.p) &&
+               (M.kind != GKOB200_PRECOND_JACOBI_SCALAR || al(M.inv_diag));
+    }
+
     int allreduce(cudaStream_t s, V* buf, size_t count)
     {
         gkob200_dist_comm* c = dm->comm;
@@ -717,11 +784,15 @@ struct DistCgSolver : SolverBase<V> {
     int update(cudaStream_t s, V* x)
     {
         DistCgParams<V> P = params(x);
-        const int grid = grid_for(n, 256, 6);
-        if (M.kind == GKOB200_PRECOND_NONE)
-            dist_cg_update<V, 0, First><<<grid, 256, 0, s>>>(P);
-        else
-            dist_cg_update<V, 1, First><<<grid, 256, 0, s>>>(P);
+        const bool wide = wide_ok(x);
+        const int grid = grid_for(wide ? n / 2 : n, 256, 6);
+        if (M.kind == GKOB200_PRECOND_NONE) {
+            if (wide) dist_cg_update<V, 0, First, true><<<grid, 256, 0, s>>>(P);
+            else dist_cg_update<V, 0, First, false><<<grid, 256, 0, s>>>(P);
+        } else {
+            if (wide) dist_cg_update<V, 1, First, true><<<grid, 256, 0, s>>>(P);
+            else dist_cg_update<V, 1, First, false><<<grid, 256, 0, s>>>(P);
+        }
         GKOB200_CHECK_LAUNCH();
         ++launch_count;
         if (P.p2p) return 0;   // exchange + scalars happened in the kernel's finaliser
@@ -737,11 +808,15 @@ struct DistCgSolver : SolverBase<V> {
     int enqueue_iteration(cudaStream_t s, V* x)
     {
         DistCgParams<V> P = params(x);
-        const int grid = grid_for(n, 256, 6);
-        if (M.kind == GKOB200_PRECOND_NONE)
-            dist_cg_direction<V, true><<<grid, 256, 0, s>>>(P);
-        else
-            dist_cg_direction<V, false><<<grid, 256, 0, s>>>(P);
+        const bool wide = wide_ok(x);
+        const int grid = grid_for(wide ? n / 2 : n, 256, 6);
+        if (M.kind == GKOB200_PRECOND_NONE) {
+            if (wide) dist_cg_direction<V, true, true><<<grid, 256, 0, s>>>(P);
+            else dist_cg_direction<V, true, false><<<grid, 256, 0, s>>>(P);
+        } else {
+            if (wide) dist_cg_direction<V, false, true><<<grid, 256, 0, s>>>(P);
+            else dist_cg_direction<V, false, false><<<grid, 256, 0, s>>>(P);
+        }
         ++launch_count;
         GKOB200_CHECK_LAUNCH();
         SpmvFusion<V> fu;

@@ -303,6 +303,23 @@ void compute_max_row_nnz(Exec exec, const array<IndexType>& row_ptrs, size_type&
     max_nnz = to_host(out.get_const_data());
 }
 template void compute_max_row_nnz<int32>(Exec, const array<int32>&, size_type&);
+// [core/matrix/ell_kernels.hpp:84-87; oracle reference/matrix/ell_kernels.cpp:222-234] — what
+// Ell::operator= runs on the SOURCE's executor: the stored columns, stride to stride
+template <typename V, typename I>
+void copy(Exec, const matrix::Ell<V, I>* source, matrix::Ell<V, I>* result)
+{
+    const size_t rows = source->get_size()[0], width = source->get_num_stored_elements_per_row();
+    if (rows == 0 || width == 0) return;
+    CUDA_OK(cudaMemcpy2DAsync(result->get_values(), result->get_stride() * sizeof(V), source->get_const_values(),
+                              source->get_stride() * sizeof(V), rows * sizeof(V), width, cudaMemcpyDeviceToDevice, nullptr));
+    CUDA_OK(cudaMemcpy2DAsync(result->get_col_idxs(), result->get_stride() * sizeof(I), source->get_const_col_idxs(),
+                              source->get_stride() * sizeof(I), rows * sizeof(I), width, cudaMemcpyDeviceToDevice, nullptr));
+}
+template void copy<double, int32>(Exec, const matrix::Ell<double, int32>*, matrix::Ell<double, int32>*);
+template void copy<float, int32>(Exec, const matrix::Ell<float, int32>*, matrix::Ell<float, int32>*);
+template void copy<double, int64>(Exec, const matrix::Ell<double, int64>*, matrix::Ell<double, int64>*);
+template void copy<float, int64>(Exec, const matrix::Ell<float, int64>*, matrix::Ell<float, int64>*);
+
 template void compute_max_row_nnz<int64>(Exec, const array<int64>&, size_type&);
 }  // namespace ell
 
