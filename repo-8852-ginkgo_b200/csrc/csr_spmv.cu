@@ -246,10 +246,8 @@ __global__ void __launch_bounds__(kRowsPerCta, rowblock_min_ctas(kBatch, sizeof(
     // "stopped" flag, this thread's two row pointers (coalesced, overlapping by one) and —
     // for the fused dot — w[row], which is only needed in the epilogue.
     int skip = 0;
-    V w_row = V(0);
     if (Fused) {
         if (fu.skip) skip = *fu.skip;
-        if (fu.out && tid < nrow) w_row = ldg(fu.w + row0 + tid);
     }
     const I my_begin = row_ptrs[row0 + min(tid, nrow)];
     const I my_end = row_ptrs[row0 + min(tid + 1, nrow)];
@@ -363,6 +361,10 @@ __global__ void __launch_bounds__(kRowsPerCta, rowblock_min_ctas(kBatch, sizeof(
     }
     if (tid < nrow) c[(row0 + tid) * c_stride] = acc;
     if (Fused && fu.out) {
+        // w[row] is fetched here, not in the prologue: in the solvers w is the vector this CTA just
+        // gathered from (the diagonal entry), so the load hits L1, and two registers less live
+        // across the row walk keep the short-row variants at 12 resident CTAs without spills
+        const V w_row = tid < nrow ? ldg(fu.w + row0 + tid) : V(0);
         // one partial per warp (no barrier), summed by finish_partials right after this launch
         if (fu.out_sq)
             store_warp_partial2(tid < nrow ? acc * w_row : V(0), tid < nrow ? acc * acc : V(0), ws_partials<V>(fu.ws),
