@@ -189,8 +189,9 @@ __device__ __forceinline__ void halo_push_cta(const HaloDev* __restrict__ H, con
 // Resident CTAs per SM the register allocation must allow.  Short-row matrices (5-pt / 7-pt:
 // ~10 KB tiles) are limited by registers, not shared memory, and the kernel needs every resident
 // tile it can get to cover HBM latency: 12 CTAs (<= 40 registers) instead of the 10 that the
-// fused / halo variants got at 44-48 registers cost 20 % of the bandwidth.
-constexpr int rowblock_min_ctas(int batch, size_t) { return batch <= 7 ? 12 : batch <= 9 ? 9 : 1; }
+// fused / halo variants got at 44-48 registers cost 20 % of the bandwidth (7-pt); the 5-entry
+// batch of the 5-pt variants fits 32 registers = 16 CTAs.
+constexpr int rowblock_min_ctas(int batch, size_t) { return batch <= 5 ? 16 : batch <= 7 ? 12 : batch <= 9 ? 9 : 1; }
 
 template <typename V, typename I, bool Advanced, bool Fused, int kBatch, bool Halo = false>
 __global__ void __launch_bounds__(kRowsPerCta, rowblock_min_ctas(kBatch, sizeof(V)))

@@ -25,6 +25,7 @@
 #include "core/components/prefix_sum_kernels.hpp"
 #include "core/distributed/matrix_kernels.hpp"
 #include "core/distributed/partition_kernels.hpp"
+#include "core/distributed/vector_kernels.hpp"
 #include "core/matrix/csr_kernels.hpp"
 #include "core/matrix/dense_kernels.hpp"
 #include "core/matrix/ell_kernels.hpp"
@@ -522,6 +523,39 @@ void build_local_nonlocal<float, int32, int64>(
 }
 
 }  // namespace distributed_matrix
+
+namespace distributed_vector {
+
+using comm_index_type = experimental::distributed::comm_index_type;
+
+// [core/distributed/vector_kernels.hpp:52-59; oracle reference/distributed/vector_kernels.cpp]
+template <typename V, typename LI, typename GI>
+void build_local(Exec, const device_matrix_data<V, GI>& input, const experimental::distributed::Partition<LI, GI>* partition,
+                 comm_index_type local_part, matrix::Dense<V>* local_mtx);
+template <>
+void build_local<double, int32, int64>(Exec, const device_matrix_data<double, int64>& input,
+                                       const experimental::distributed::Partition<int32, int64>* p,
+                                       comm_index_type local_part, matrix::Dense<double>* local_mtx)
+{
+    B200(gkob200_dist_vector_build_local_f64(kStream, (int64_t)input.get_num_elems(), input.get_const_row_idxs(),
+                                             input.get_const_col_idxs(), input.get_const_values(),
+                                             (int64_t)p->get_num_ranges(), p->get_range_bounds(), p->get_part_ids(),
+                                             p->get_range_starting_indices(), (int32_t)local_part,
+                                             local_mtx->get_values(), (int64_t)local_mtx->get_stride()));
+}
+template <>
+void build_local<float, int32, int64>(Exec, const device_matrix_data<float, int64>& input,
+                                      const experimental::distributed::Partition<int32, int64>* p,
+                                      comm_index_type local_part, matrix::Dense<float>* local_mtx)
+{
+    B200(gkob200_dist_vector_build_local_f32(kStream, (int64_t)input.get_num_elems(), input.get_const_row_idxs(),
+                                             input.get_const_col_idxs(), input.get_const_values(),
+                                             (int64_t)p->get_num_ranges(), p->get_range_bounds(), p->get_part_ids(),
+                                             p->get_range_starting_indices(), (int32_t)local_part,
+                                             local_mtx->get_values(), (int64_t)local_mtx->get_stride()));
+}
+
+}  // namespace distributed_vector
 
 }  // namespace cuda
 }  // namespace kernels

@@ -9,9 +9,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def declared_symbols():
-    out = subprocess.run(["gcc", "-E", "-P", os.path.join(ROOT, "include", "gko_b200.h")],
-                         check=True, capture_output=True, text=True).stdout
-    return sorted(set(re.findall(r"\b(gkob200_[a-z0-9_]+)\s*\(", out)))
+    syms = set()
+    for header in ("gko_b200.h", "gko_b200_solver.h"):
+        out = subprocess.run(["gcc", "-E", "-P", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "include", header)],
+                             check=True, capture_output=True, text=True).stdout
+        syms |= set(re.findall(r"\b(gkob200_[a-z0-9_]+)\s*\(", out))
+    return sorted(syms)
 
 
 def test_header_is_plain_c():
