@@ -195,3 +195,26 @@ def test_merge_path_rows_spanning_many_tiles(gko, exec_, ora, n, row_len):
     # twice through the same (planned) descriptor: carries of the first launch must not leak
     got2, _ = gpu_apply(gko, exec_, rp, ci, va, (n, m), b, "merge_path", -0.5, 3.0, c0)
     assert np.array_equal(got, got2)
+
+
+@pytest.mark.parametrize("kind,dims", [("27pt", (16, 16, 16)), ("27pt", (24, 20, 12)), ("7pt", (32, 16, 8)),
+                                       ("5pt", (64, 64, 1)), ("27pt", (17, 16, 16)), ("7pt", (16, 16, 18))])
+@pytest.mark.parametrize("fmt", ["csr", "ell", "sellp"])
+def test_spmm_lattice_tile_order_is_bit_identical(gko, exec_, ora, kind, dims, fmt):
+    """Regular grids switch the SpMM kernel to the lattice-aware tile order (warps of a CTA own row
+    tiles that are neighbours across grid lines / planes; spmm.cuh); grids that do not divide
+    evenly keep the consecutive order.  Either way every (row, column) is summed in storage order:
+    the result equals the oracle's bit for bit, with and without alpha / beta."""
+    rp, ci, va, n = gko.gen.stencil_csr(kind, *dims)
+    rng = np.random.default_rng(3)
+    b = rng.standard_normal((n, 32))
+    c0 = rng.standard_normal((n, 32))
+    A = gko.matrix.Csr.from_arrays(exec_, (n, n), rp, ci, va)
+    M = A if fmt == "csr" else A.convert_to(fmt)
+    db = gko.matrix.Dense.from_numpy(exec_, b)
+    dc = gko.matrix.Dense.create(exec_, (n, 32))
+    M.apply(db, dc)
+    assert np.array_equal(dc.to_numpy(), ora.csr_spmv(rp, ci, va, b))
+    dc = gko.matrix.Dense.from_numpy(exec_, c0)
+    M.apply(gko.matrix.Dense.scalar(exec_, -0.75), db, gko.matrix.Dense.scalar(exec_, 1.5), dc)
+    assert np.array_equal(dc.to_numpy(), ora.csr_spmv(rp, ci, va, b, -0.75, 1.5, c0))
