@@ -212,7 +212,9 @@ struct SolverBase : gkob200_solver {
     {
         n = A.n_rows;
         if (A.n_rows != A.n_cols) return GKOB200_EINVAL;
-        chunk = stop.check_every > 0 ? stop.check_every : 8;
+        // iterations per CUDA graph / per host poll; bounded so that a huge check_every cannot
+        // turn into a graph of hundreds of thousands of nodes
+        chunk = stop.check_every > 0 ? (stop.check_every < 512 ? stop.check_every : 512) : 8;
         int rc;
         if ((rc = state.alloc(sizeof(SolverState)))) return rc;
         if ((rc = status.alloc(static_cast<size_t>(k) + 16))) return rc;
