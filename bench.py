@@ -216,10 +216,10 @@ STENCIL_DIAG_REF = {"7pt": 6.0, "27pt": 26.0}
 def ncu_traffic(fmt, grid):
     """DRAM read + write bytes per launch of the dominant kernel.  ncu cannot run inside a timed
     benchmark, so this is NOT measured in this run: it is read from the committed `ncu --set full`
-    capture of the same kernel and matrix (profiles/r01_traffic.json, written by
-    tools/ncu_summary.py from profiles/r01_csr_spmv_rowblock_tma_v3_ncu_full.txt)."""
+    capture of the same kernel and matrix (profiles/r02_traffic.json, written by
+    tools/ncu_summary.py from profiles/r02_csr_spmv_rowblock_tma_ncu_full.txt)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             return json.load(f).get(f"{fmt}_27pt_{grid}")
     except (OSError, ValueError):
         return None
@@ -337,7 +337,7 @@ def main():
                      "bytes_per_launch": spmv_bytes, "us_per_launch": spmv_s * 1e6,
                      "traffic": ncu_traffic(args.format, g),
                      "traffic_source": "committed ncu --set full capture of this kernel on this matrix "
-                                       "(profiles/r01_csr_spmv_rowblock_tma_v3_ncu_full.txt), not measured in this run"},
+                                       "(profiles/r02_csr_spmv_rowblock_tma_ncu_full.txt), not measured in this run"},
         "cg_iteration": {"us": 1e6 * secs / (args.steps * iters), "model_bytes": it_bytes,
                          "model_gbs": it_bytes * args.steps * iters / secs / 1e9,
                          "frac_of_peak": it_bytes * args.steps * iters / secs / 1e9 / peak},
