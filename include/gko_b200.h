@@ -302,6 +302,18 @@ GKOB200_DECL_JACOBI_SCALAR(f32, float)
     int gkob200_fcg_step_2_##V(void* stream, int64_t n, int64_t k, VT* x, int64_t x_stride, VT* r, VT* t,          \
                                const VT* p, const VT* q, int64_t stride, const VT* beta, const VT* rho,            \
                                const uint8_t* stop_status);                                                       \
+    /* BiCG step kernels [ref: core/solver/bicg_kernels.hpp; replaced                               \
+     * common/unified/solver/bicg_kernels.cpp:53-170]: r2/z2/p2/q2 belong to the transposed system; the           \
+     * host loop (core/solver/bicg.cpp:160-243) builds A^T with csr::transpose.  solver::Ir needs no kernel of     \
+     * its own beyond ir::initialize (a status reset: gkob200_set_all_statuses / fill_array). */                   \
+    int gkob200_bicg_initialize_##V(void* stream, int64_t n, int64_t k, const VT* b, int64_t b_stride, VT* r,      \
+                                    VT* z, VT* p, VT* q, VT* r2, VT* z2, VT* p2, VT* q2, int64_t stride,           \
+                                    VT* prev_rho, VT* rho, uint8_t* stop_status);                                 \
+    int gkob200_bicg_step_1_##V(void* stream, int64_t n, int64_t k, VT* p, const VT* z, VT* p2, const VT* z2,      \
+                                int64_t stride, const VT* rho, const VT* prev_rho, const uint8_t* stop_status);    \
+    int gkob200_bicg_step_2_##V(void* stream, int64_t n, int64_t k, VT* x, int64_t x_stride, VT* r, VT* r2,        \
+                                const VT* p, const VT* q, const VT* q2, int64_t stride, const VT* beta,            \
+                                const VT* rho, const uint8_t* stop_status);                                       \
     int gkob200_cgs_initialize_##V(void* stream, int64_t n, int64_t k, const VT* b, int64_t b_stride, VT* r,       \
                                    VT* r_tld, VT* p, VT* q, VT* u, VT* u_hat, VT* v_hat, VT* t, int64_t stride,    \
                                    VT* alpha, VT* beta, VT* gamma, VT* rho_prev, VT* rho, uint8_t* stop_status);   \
@@ -370,6 +382,11 @@ int gkob200_jacobi_find_blocks_i32(void* stream, int64_t n_rows, const int32_t* 
                                           const int32_t* col_idxs, const VT* values, int64_t num_blocks,           \
                                           const int32_t* block_pointers, int64_t block_offset,                     \
                                           int64_t group_offset, int group_power, VT* blocks);                      \
+    /* out block = transpose of the stored block [ref: jacobi::transpose_jacobi / conj_transpose_jacobi,        \
+     * core/preconditioner/jacobi_kernels.hpp:114-134] (what solver::Bicg asks of its preconditioner) */          \
+    int gkob200_jacobi_block_transpose_##V(void* stream, int64_t num_blocks, const int32_t* block_pointers,        \
+                                           const VT* blocks, int64_t block_offset, int64_t group_offset,           \
+                                           int group_power, VT* out_blocks);                                      \
     int gkob200_jacobi_block_simple_apply_##V(void* stream, int64_t num_blocks, const int32_t* block_pointers,     \
                                               const VT* blocks, int64_t block_offset, int64_t group_offset,        \
                                               int group_power, int64_t n, int64_t k, const VT* b, int64_t b_stride, \

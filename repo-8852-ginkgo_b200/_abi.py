@@ -119,6 +119,10 @@ def declare(lib):
         d(f"gkob200_row_len_histogram_{I}", [vp, vp, i64, u64, u64, C.c_int, vp])
     # Krylov step kernels
     for V, T in VT.items():
+        d(f"gkob200_bicg_initialize_{V}", [vp, i64, i64, vp, i64] + [vp] * 8 + [i64] + [vp] * 3)
+        d(f"gkob200_bicg_step_1_{V}", [vp, i64, i64, vp, vp, vp, vp, i64, vp, vp, vp])
+        d(f"gkob200_bicg_step_2_{V}", [vp, i64, i64, vp, i64, vp, vp, vp, vp, vp, i64, vp, vp, vp])
+        d(f"gkob200_jacobi_block_transpose_{V}", [vp, i64, vp, vp, i64, i64, C.c_int, vp])
         d(f"gkob200_fcg_initialize_{V}", [vp, i64, i64, vp, i64] + [vp] * 5 + [i64] + [vp] * 4)
         d(f"gkob200_fcg_step_1_{V}", [vp, i64, i64, vp, vp, i64, vp, vp, vp])
         d(f"gkob200_fcg_step_2_{V}", [vp, i64, i64, vp, i64, vp, vp, vp, vp, i64, vp, vp, vp])

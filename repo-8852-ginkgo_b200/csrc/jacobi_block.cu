@@ -271,6 +271,24 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta)
 
 using namespace gkob200;
 
+// out block = transpose of the stored (inverse) block, same storage scheme
+// [ref: jacobi::transpose_jacobi / conj_transpose_jacobi, reference/preconditioner/jacobi_kernels.cpp:629-690]
+template <typename V>
+__global__ void __launch_bounds__(32 * kWarpsPerCta)
+    block_transpose(int64_t num_blocks, const int32_t* __restrict__ bptrs, const V* __restrict__ blocks,
+                    int64_t block_offset, int64_t group_offset, int group_power, V* __restrict__ out)
+{
+    const int64_t blk = static_cast<int64_t>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
+    if (blk >= num_blocks) return;
+    const int lane = threadIdx.x & 31;
+    const int bs = bptrs[blk + 1] - bptrs[blk];
+    const int64_t gs_mask = (int64_t(1) << group_power) - 1;
+    const int64_t stride = block_offset << group_power;
+    const int64_t base = group_offset * (blk >> group_power) + block_offset * (blk & gs_mask);
+    for (int c = 0; c < bs; ++c)
+        if (lane < bs) out[base + c + lane * stride] = blocks[base + lane + c * stride];
+}
+
 extern "C" {
 
 size_t gkob200_jacobi_find_blocks_workspace_bytes(int64_t n_rows)
@@ -341,6 +359,18 @@ int gkob200_jacobi_find_blocks_i32(void* stream, int64_t n, const int32_t* row_p
         block_generate<VT><<<static_cast<unsigned>(ceildiv(num_blocks, kWarpsPerCta)), 32 * kWarpsPerCta, 0,      \
                              as_stream(stream)>>>(num_blocks, row_ptrs, col_idxs, values, block_pointers,         \
                                                   block_offset, group_offset, group_power, blocks);               \
+        GKOB200_CHECK_LAUNCH();                                                                                  \
+        return 0;                                                                                                \
+    }                                                                                                            \
+    int gkob200_jacobi_block_transpose_##V(void* stream, int64_t num_blocks, const int32_t* block_pointers,       \
+                                           const VT* blocks, int64_t block_offset, int64_t group_offset,          \
+                                           int group_power, VT* out_blocks)                                      \
+    {                                                                                                            \
+        if (num_blocks < 0) return GKOB200_EINVAL;                                                               \
+        if (num_blocks == 0) return 0;                                                                           \
+        block_transpose<VT><<<static_cast<unsigned>(ceildiv(num_blocks, kWarpsPerCta)), 32 * kWarpsPerCta, 0,     \
+                              as_stream(stream)>>>(num_blocks, block_pointers, blocks, block_offset, group_offset, \
+                                                   group_power, out_blocks);                                     \
         GKOB200_CHECK_LAUNCH();                                                                                  \
         return 0;                                                                                                \
     }                                                                                                            \

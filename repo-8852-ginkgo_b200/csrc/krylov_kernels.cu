@@ -165,6 +165,56 @@ int fcg_step_2(void* st, int64_t n, int64_t k, V* x, int64_t xs, V* r, V* t, con
     });
 }
 
+// BiCG step kernels [ref: common/unified/solver/bicg_kernels.cpp:53-170; the arithmetic of
+// reference/solver/bicg_kernels.cpp].  The transposed system matrix and preconditioner are the
+// caller's (core/solver/bicg.cpp:160-185 builds them with csr::transpose).
+template <typename V>
+int bicg_initialize(void* st, int64_t n, int64_t k, const V* b, int64_t bs, V* r, V* z, V* p, V* q, V* r2, V* z2, V* p2,
+                    V* q2, int64_t s, V* prev_rho, V* rho, uint8_t* stop)
+{
+    if (n < 0 || k < 0) return GKOB200_EINVAL;
+    if (k == 0) return 0;
+    int rc = launch_2d(as_stream(st), 1, k, [=] __device__(int64_t, int64_t j) {
+        rho[j] = V(0);
+        prev_rho[j] = V(1);
+        stop[j] = 0;
+    });
+    if (rc) return rc;
+    return launch_2d(as_stream(st), n, k, [=] __device__(int64_t i, int64_t j) {
+        r[i * s + j] = r2[i * s + j] = b[i * bs + j];
+        z[i * s + j] = p[i * s + j] = q[i * s + j] = z2[i * s + j] = p2[i * s + j] = q2[i * s + j] = V(0);
+    });
+}
+
+template <typename V>
+int bicg_step_1(void* st, int64_t n, int64_t k, V* p, const V* z, V* p2, const V* z2, int64_t s, const V* rho,
+                const V* prev_rho, const uint8_t* stop)
+{
+    if (n < 0 || k < 0) return GKOB200_EINVAL;
+    return launch_2d(as_stream(st), n, k, [=] __device__(int64_t i, int64_t j) {
+        if (status_has_stopped(stop[j])) return;
+        const V pr = prev_rho[j];
+        const V tmp = pr == V(0) ? V(0) : div_rn(rho[j], pr);   // safe_divide
+        p[i * s + j] = add_rn(z[i * s + j], mul_rn(tmp, p[i * s + j]));
+        p2[i * s + j] = add_rn(z2[i * s + j], mul_rn(tmp, p2[i * s + j]));
+    });
+}
+
+template <typename V>
+int bicg_step_2(void* st, int64_t n, int64_t k, V* x, int64_t xs, V* r, V* r2, const V* p, const V* q, const V* q2,
+                int64_t s, const V* beta, const V* rho, const uint8_t* stop)
+{
+    if (n < 0 || k < 0) return GKOB200_EINVAL;
+    return launch_2d(as_stream(st), n, k, [=] __device__(int64_t i, int64_t j) {
+        if (status_has_stopped(stop[j])) return;
+        const V be = beta[j];
+        const V tmp = be == V(0) ? V(0) : div_rn(rho[j], be);   // safe_divide
+        x[i * xs + j] = add_rn(x[i * xs + j], mul_rn(tmp, p[i * s + j]));
+        r[i * s + j] = sub_rn(r[i * s + j], mul_rn(tmp, q[i * s + j]));
+        r2[i * s + j] = sub_rn(r2[i * s + j], mul_rn(tmp, q2[i * s + j]));
+    });
+}
+
 template <typename V>
 int cgs_initialize(void* st, int64_t n, int64_t k, const V* b, int64_t bs, V* r, V* r_tld, V* p, V* q, V* u, V* u_hat,
                    V* v_hat, V* t, int64_t s, V* alpha, V* beta, V* gamma, V* rho_prev, V* rho, uint8_t* stop)
@@ -407,6 +457,17 @@ extern "C" {
     int gkob200_fcg_step_2_##V(void* st, int64_t n, int64_t k, VT* x, int64_t xs, VT* r, VT* t, const VT* p,       \
                                const VT* q, int64_t s, const VT* beta, const VT* rho, const uint8_t* stop)         \
     { return fcg_step_2<VT>(st, n, k, x, xs, r, t, p, q, s, beta, rho, stop); }                                    \
+    int gkob200_bicg_initialize_##V(void* st, int64_t n, int64_t k, const VT* b, int64_t bs, VT* r, VT* z, VT* p,  \
+                                    VT* q, VT* r2, VT* z2, VT* p2, VT* q2, int64_t s, VT* prev_rho, VT* rho,       \
+                                    uint8_t* stop)                                                                \
+    { return bicg_initialize<VT>(st, n, k, b, bs, r, z, p, q, r2, z2, p2, q2, s, prev_rho, rho, stop); }           \
+    int gkob200_bicg_step_1_##V(void* st, int64_t n, int64_t k, VT* p, const VT* z, VT* p2, const VT* z2,          \
+                                int64_t s, const VT* rho, const VT* prev_rho, const uint8_t* stop)                 \
+    { return bicg_step_1<VT>(st, n, k, p, z, p2, z2, s, rho, prev_rho, stop); }                                    \
+    int gkob200_bicg_step_2_##V(void* st, int64_t n, int64_t k, VT* x, int64_t xs, VT* r, VT* r2, const VT* p,     \
+                                const VT* q, const VT* q2, int64_t s, const VT* beta, const VT* rho,               \
+                                const uint8_t* stop)                                                              \
+    { return bicg_step_2<VT>(st, n, k, x, xs, r, r2, p, q, q2, s, beta, rho, stop); }                              \
     int gkob200_cgs_initialize_##V(void* st, int64_t n, int64_t k, const VT* b, int64_t bs, VT* r, VT* r_tld,      \
                                    VT* p, VT* q, VT* u, VT* u_hat, VT* v_hat, VT* t, int64_t s, VT* alpha,         \
                                    VT* beta, VT* gamma, VT* rho_prev, VT* rho, uint8_t* stop)                      \

@@ -30,7 +30,9 @@
 #include "core/matrix/ell_kernels.hpp"
 #include "core/matrix/sellp_kernels.hpp"
 #include "core/preconditioner/jacobi_kernels.hpp"
+#include "core/solver/bicg_kernels.hpp"
 #include "core/solver/bicgstab_kernels.hpp"
+#include "core/solver/ir_kernels.hpp"
 #include "core/solver/cg_kernels.hpp"
 #include "core/solver/cgs_kernels.hpp"
 #include "core/solver/fcg_kernels.hpp"
@@ -126,6 +128,9 @@ TYPED(dense_compute_sqrt)
 TYPED(cg_initialize)
 TYPED(cg_step_1)
 TYPED(cg_step_2)
+TYPED(bicg_initialize)
+TYPED(bicg_step_1)
+TYPED(bicg_step_2)
 TYPED(fcg_initialize)
 TYPED(fcg_step_1)
 TYPED(fcg_step_2)
@@ -153,6 +158,7 @@ TYPED(jacobi_scalar_apply)
 TYPED(jacobi_block_generate)
 TYPED(jacobi_block_simple_apply)
 TYPED(jacobi_block_apply)
+TYPED(jacobi_block_transpose)
 template <typename... A> inline int csr_extract_diagonal(double, A... a) { return gkob200_csr_extract_diagonal_f64_i32(a...); }
 template <typename... A> inline int csr_extract_diagonal(float, A... a) { return gkob200_csr_extract_diagonal_f32_i32(a...); }
 }  // namespace t
@@ -500,6 +506,57 @@ INST_CG(float)
 
 }  // namespace cg
 
+// [core/solver/bicg_kernels.hpp; the host loop core/solver/bicg.cpp:120-243 transposes the system
+// matrix with csr::transpose and the preconditioner with Transposable::conj_transpose]
+namespace bicg {
+
+template <typename V>
+void initialize(Exec, const D<V>* b, D<V>* r, D<V>* z, D<V>* p, D<V>* q, D<V>* prev_rho, D<V>* rho, D<V>* r2, D<V>* z2,
+                D<V>* p2, D<V>* q2, array<stopping_status>* stop_status)
+{
+    B200(t::bicg_initialize(V{}, kStream, (int64_t)b->get_size()[0], (int64_t)b->get_size()[1], b->get_const_values(),
+                            (int64_t)b->get_stride(), r->get_values(), z->get_values(), p->get_values(), q->get_values(),
+                            r2->get_values(), z2->get_values(), p2->get_values(), q2->get_values(),
+                            (int64_t)r->get_stride(), prev_rho->get_values(), rho->get_values(), status_ptr(stop_status)));
+}
+template <typename V>
+void step_1(Exec, D<V>* p, const D<V>* z, D<V>* p2, const D<V>* z2, const D<V>* rho, const D<V>* prev_rho,
+            const array<stopping_status>* stop_status)
+{
+    B200(t::bicg_step_1(V{}, kStream, (int64_t)p->get_size()[0], (int64_t)p->get_size()[1], p->get_values(),
+                        z->get_const_values(), p2->get_values(), z2->get_const_values(), (int64_t)p->get_stride(),
+                        rho->get_const_values(), prev_rho->get_const_values(), status_ptr(stop_status)));
+}
+template <typename V>
+void step_2(Exec, D<V>* x, D<V>* r, D<V>* r2, const D<V>* p, const D<V>* q, const D<V>* q2, const D<V>* beta,
+            const D<V>* rho, const array<stopping_status>* stop_status)
+{
+    B200(t::bicg_step_2(V{}, kStream, (int64_t)x->get_size()[0], (int64_t)x->get_size()[1], x->get_values(),
+                        (int64_t)x->get_stride(), r->get_values(), r2->get_values(), p->get_const_values(),
+                        q->get_const_values(), q2->get_const_values(), (int64_t)r->get_stride(), beta->get_const_values(),
+                        rho->get_const_values(), status_ptr(stop_status)));
+}
+#define INST_BICG(V)                                                                                                  \
+    template void initialize<V>(Exec, const D<V>*, D<V>*, D<V>*, D<V>*, D<V>*, D<V>*, D<V>*, D<V>*, D<V>*, D<V>*,      \
+                                D<V>*, array<stopping_status>*);                                                      \
+    template void step_1<V>(Exec, D<V>*, const D<V>*, D<V>*, const D<V>*, const D<V>*, const D<V>*,                    \
+                            const array<stopping_status>*);                                                           \
+    template void step_2<V>(Exec, D<V>*, D<V>*, D<V>*, const D<V>*, const D<V>*, const D<V>*, const D<V>*,             \
+                            const D<V>*, const array<stopping_status>*);
+INST_BICG(double)
+INST_BICG(float)
+
+}  // namespace bicg
+
+// [core/solver/ir_kernels.hpp:54-56]: solver::Ir's only kernel resets the stopping status
+namespace ir {
+void initialize(Exec, array<stopping_status>* stop_status)
+{
+    const uint8 zero = 0;   // stopping_status::reset()
+    B200(gkob200_fill_array(kStream, status_ptr(stop_status), (int64_t)stop_status->get_num_elems(), 1, &zero));
+}
+}  // namespace ir
+
 namespace fcg {
 
 template <typename V>
@@ -845,6 +902,22 @@ void apply(Exec, size_type num_blocks, uint32, const preconditioner::block_inter
                                b->get_const_values(), (int64_t)b->get_stride(), beta->get_const_values(), x->get_values(),
                                (int64_t)x->get_stride()));
 }
+template <typename V, typename I>
+void transpose_jacobi(Exec, size_type num_blocks, uint32, const array<precision_reduction>&, const array<I>& block_ptrs,
+                      const array<V>& blocks, const preconditioner::block_interleaved_storage_scheme<I>& scheme,
+                      array<V>& out_blocks)
+{
+    B200(t::jacobi_block_transpose(V{}, kStream, (int64_t)num_blocks, block_ptrs.get_const_data(), blocks.get_const_data(),
+                                   (int64_t)scheme.block_offset, (int64_t)scheme.group_offset, (int)scheme.group_power,
+                                   out_blocks.get_data()));
+}
+template <typename V, typename I>
+void conj_transpose_jacobi(Exec exec, size_type num_blocks, uint32 mbs, const array<precision_reduction>& prec,
+                           const array<I>& block_ptrs, const array<V>& blocks,
+                           const preconditioner::block_interleaved_storage_scheme<I>& scheme, array<V>& out_blocks)
+{
+    transpose_jacobi<V, I>(exec, num_blocks, mbs, prec, block_ptrs, blocks, scheme, out_blocks);   // real value types
+}
 void initialize_precisions(Exec exec, const array<precision_reduction>& source, array<precision_reduction>& precisions)
 {
     // Blocks are stored in full precision only on this path.  A request for reduced or
@@ -877,6 +950,18 @@ void initialize_precisions(Exec exec, const array<precision_reduction>& source, 
                                   const D<V>*, const D<V>*, D<V>*);
 INST_JAC(double)
 INST_JAC(float)
+#define INST_JACT(V)                                                                                               \
+    template void transpose_jacobi<V, int32>(Exec, size_type, uint32, const array<precision_reduction>&,            \
+                                             const array<int32>&, const array<V>&,                                  \
+                                             const preconditioner::block_interleaved_storage_scheme<int32>&,        \
+                                             array<V>&);                                                            \
+    template void conj_transpose_jacobi<V, int32>(Exec, size_type, uint32, const array<precision_reduction>&,       \
+                                                  const array<int32>&, const array<V>&,                             \
+                                                  const preconditioner::block_interleaved_storage_scheme<int32>&,   \
+                                                  array<V>&);
+INST_JACT(double)
+INST_JACT(float)
+
 
 }  // namespace jacobi
 

@@ -255,6 +255,48 @@ int main(int argc, char** argv)
         check_solver<gko::solver::Gmres<V>>("Gmres", ref, cuda, A, b.get(), bs);
         check_solver<gko::solver::Fcg<V>>("Fcg", ref, cuda, A, b.get(), bs);
         check_solver<gko::solver::Cgs<V>>("Cgs", ref, cuda, A, b.get(), bs);
+        check_solver<gko::solver::Bicg<V>>("Bicg", ref, cuda, A, b.get(), bs);
+    }
+    // solver::Ir: damped Jacobi (inner solver = scalar Jacobi) and plain Richardson (identity)
+    for (int variant = 0; variant < 2; ++variant) {
+        int iters[2];
+        std::unique_ptr<Dense> xs[2];
+        std::shared_ptr<gko::Executor> execs[2] = {ref, cuda};
+        for (int e = 0; e < 2; ++e) {
+            auto exec = execs[e];
+            auto Ae = gko::share(gko::clone(exec, A));
+            auto be = gko::clone(exec, b);
+            auto x = Dense::create(exec, b->get_size());
+            x->fill(0.0);
+            auto it_crit = gko::share(gko::stop::Iteration::build().with_max_iters(variant == 0 ? 400u : 60u).on(exec));
+            auto res_crit = gko::share(gko::stop::ResidualNorm<V>::build().with_reduction_factor(1e-8).on(exec));
+            auto logger = gko::share(gko::log::Convergence<V>::create(exec));
+            it_crit->add_logger(logger);
+            res_crit->add_logger(logger);
+            std::shared_ptr<gko::LinOp> solver;
+            if (variant == 0) {
+                solver = gko::solver::Ir<V>::build()
+                             .with_solver(gko::share(gko::preconditioner::Jacobi<V, I>::build().with_max_block_size(1u).on(exec)))
+                             .with_relaxation_factor(0.9)
+                             .with_criteria(it_crit, res_crit)
+                             .on(exec)
+                             ->generate(Ae);
+            } else {
+                solver = gko::solver::Ir<V>::build()
+                             .with_relaxation_factor(0.03)
+                             .with_criteria(it_crit, res_crit)
+                             .on(exec)
+                             ->generate(Ae);
+            }
+            solver->apply(be.get(), x.get());
+            iters[e] = static_cast<int>(logger->get_num_iterations());
+            xs[e] = std::move(x);
+        }
+        char what[160];
+        std::snprintf(what, sizeof(what), "Ir (%s): iterations ref %d / cuda %d", variant == 0 ? "damped Jacobi" : "Richardson",
+                      iters[0], iters[1]);
+        EXPECT(std::abs(iters[0] - iters[1]) <= 2, what);
+        EXPECT(rel_diff(xs[1].get(), xs[0].get()) <= 1e-8, "Ir: solution");
     }
     std::printf("--- setup kernels\n");
     {

@@ -181,3 +181,52 @@ def test_fcg_cgs_reference_solve_kats(gko, exec_, dtype, kind, case):
     s.apply(db, dx)
     tol = np.sqrt(kat.rtol(dtype)) if tol_mult == 0.0 else kat.rtol(dtype) * tol_mult
     assert kat.rel_frobenius(dx.to_numpy(), expect) <= tol
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_bicg_step_kernels_match_the_reference_arithmetic(gko, exec_, dtype):
+    """bicg::{initialize, step_1, step_2} (common/unified/solver/bicg_kernels.cpp:53-170) through the
+    C-ABI against the same arithmetic in numpy (rounded product, rounded sum: bit-identical),
+    including a stopped column and the safe_divide(·, 0) = 0 branches."""
+    import ctypes as C
+    import torch
+    lib, V = gko.lib, ("f64" if dtype == np.float64 else "f32")
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    n, k = 1000, 3
+    rng = np.random.default_rng(5)
+    dev = exec_.device
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    P = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    b = rng.standard_normal((n, k)).astype(dtype)
+    vec = {nm: T(rng.standard_normal((n, k)).astype(dtype)) for nm in ("r", "z", "p", "q", "r2", "z2", "p2", "q2")}
+    prev_rho, rho = torch.empty(k, dtype=tdt, device=dev), torch.empty(k, dtype=tdt, device=dev)
+    stop = torch.full((k,), 7, dtype=torch.uint8, device=dev)
+    db = T(b)
+    assert getattr(lib, f"gkob200_bicg_initialize_{V}")(None, n, k, P(db), k, *[P(vec[nm]) for nm in
+                                                      ("r", "z", "p", "q", "r2", "z2", "p2", "q2")], k,
+                                                      P(prev_rho), P(rho), P(stop)) == 0
+    assert np.array_equal(vec["r"].cpu().numpy(), b) and np.array_equal(vec["r2"].cpu().numpy(), b)
+    for nm in ("z", "p", "q", "z2", "p2", "q2"):
+        assert not vec[nm].any()
+    assert rho.cpu().tolist() == [0, 0, 0] and prev_rho.cpu().tolist() == [1, 1, 1] and stop.cpu().tolist() == [0, 0, 0]
+    # step_1 / step_2 on random state; column 1 stopped, column 2 divides by zero
+    st = {nm: rng.standard_normal((n, k)).astype(dtype) for nm in ("x", "r", "r2", "p", "q", "q2", "z", "z2", "p2")}
+    rho_h = np.array([0.7, -1.3, 2.0], dtype)
+    prev_h = np.array([1.9, 0.4, 0.0], dtype)
+    beta_h = np.array([-0.6, 2.2, 0.0], dtype)
+    stop_h = np.array([0, 0x41, 0], np.uint8)
+    d = {nm: T(a) for nm, a in st.items()}
+    d_rho, d_prev, d_beta, d_stop = T(rho_h), T(prev_h), T(beta_h), T(stop_h)
+    assert getattr(lib, f"gkob200_bicg_step_1_{V}")(None, n, k, P(d["p"]), P(d["z"]), P(d["p2"]), P(d["z2"]), k,
+                                                  P(d_rho), P(d_prev), P(d_stop)) == 0
+    tmp = np.where(prev_h == 0, dtype(0), rho_h / np.where(prev_h == 0, dtype(1), prev_h)).astype(dtype)
+    live = stop_h == 0
+    want_p = np.where(live, st["z"] + (tmp * st["p"]).astype(dtype), st["p"]).astype(dtype)
+    want_p2 = np.where(live, st["z2"] + (tmp * st["p2"]).astype(dtype), st["p2"]).astype(dtype)
+    assert np.array_equal(d["p"].cpu().numpy(), want_p) and np.array_equal(d["p2"].cpu().numpy(), want_p2)
+    assert getattr(lib, f"gkob200_bicg_step_2_{V}")(None, n, k, P(d["x"]), k, P(d["r"]), P(d["r2"]), P(d["p"]), P(d["q"]),
+                                                  P(d["q2"]), k, P(d_beta), P(d_rho), P(d_stop)) == 0
+    t2 = np.where(beta_h == 0, dtype(0), rho_h / np.where(beta_h == 0, dtype(1), beta_h)).astype(dtype)
+    assert np.array_equal(d["x"].cpu().numpy(), np.where(live, st["x"] + (t2 * want_p).astype(dtype), st["x"]).astype(dtype))
+    assert np.array_equal(d["r"].cpu().numpy(), np.where(live, st["r"] - (t2 * st["q"]).astype(dtype), st["r"]).astype(dtype))
+    assert np.array_equal(d["r2"].cpu().numpy(), np.where(live, st["r2"] - (t2 * st["q2"]).astype(dtype), st["r2"]).astype(dtype))
