@@ -378,6 +378,9 @@ __global__ void __launch_bounds__(kRowsPerCta, rowblock_min_ctas(kBatch, sizeof(
 // ---------------------------------------------------------------------------
 // merge-path kernel (single right-hand side)
 // ---------------------------------------------------------------------------
+#ifndef GKOB200_MP_MIN_CTAS
+#define GKOB200_MP_MIN_CTAS 1
+#endif
 constexpr int kMpThreads = 256;
 constexpr int kMpItems = 9;                            // merge items per thread (odd: conflict-free)
 constexpr int kMpTile = kMpThreads * kMpItems;         // merge items per CTA
@@ -402,7 +405,7 @@ __device__ __forceinline__ int64_t merge_path_search(int64_t diag, const P row_e
 }
 
 template <typename V, typename I, bool Advanced>
-__global__ void __launch_bounds__(kMpThreads)
+__global__ void __launch_bounds__(kMpThreads, GKOB200_MP_MIN_CTAS)
     csr_spmv_merge(int64_t n_rows, int64_t nnz, const I* __restrict__ row_ptrs, const I* __restrict__ col_idxs,
                    const V* __restrict__ values, const V* __restrict__ b, int64_t b_stride,
                    const V* __restrict__ alpha_p, const V* __restrict__ beta_p, V* __restrict__ c,
@@ -786,12 +789,21 @@ int csr_spmv_launch(cudaStream_t s, int64_t n_rows, int64_t n_cols, int64_t nnz,
         const char* f = getenv("GKOB200_MP_KEEP_FRAC");
         return f ? static_cast<float>(atof(f)) : 1.0f;
     }();
+    // resident CTAs per SM are a tuning knob through a dynamic shared-memory pad (A/B on the box)
+    static const size_t mp_pad = [] {
+        const char* e = getenv("GKOB200_MP_PAD_KB");
+        return e ? static_cast<size_t>(atoi(e)) * 1024 : size_t(0);
+    }();
+    if (mp_pad > 16 * 1024) {
+        cudaFuncSetAttribute(csr_spmv_merge<V, I, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(mp_pad));
+        cudaFuncSetAttribute(csr_spmv_merge<V, I, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(mp_pad));
+    }
     if (adv)
-        csr_spmv_merge<V, I, true><<<static_cast<unsigned>(n_tiles), kMpThreads, 0, s>>>(
+        csr_spmv_merge<V, I, true><<<static_cast<unsigned>(n_tiles), kMpThreads, mp_pad, s>>>(
             n_rows, nnz, row_ptrs, col_idxs, values, b, b_stride, alpha, beta, c, c_stride, carry_row,
             carry_val, plan, keep_frac);
     else
-        csr_spmv_merge<V, I, false><<<static_cast<unsigned>(n_tiles), kMpThreads, 0, s>>>(
+        csr_spmv_merge<V, I, false><<<static_cast<unsigned>(n_tiles), kMpThreads, mp_pad, s>>>(
             n_rows, nnz, row_ptrs, col_idxs, values, b, b_stride, alpha, beta, c, c_stride, carry_row,
             carry_val, plan, keep_frac);
     GKOB200_CHECK_LAUNCH();

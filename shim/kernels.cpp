@@ -223,6 +223,16 @@ void sort_by_column_index(Exec, matrix::Csr<V, I>* to_sort)
     B200(t::csr_sort_by_column_index(V{}, I{}, kStream, n, m, nnz, to_sort->get_const_row_ptrs(), to_sort->get_col_idxs(),
                                      to_sort->get_values(), scratch().get(wsb), wsb));
 }
+// real value types: the conjugate transpose is the transpose (what solver::Bicg asks for)
+template <typename V, typename I>
+void conj_transpose(Exec exec, const matrix::Csr<V, I>* orig, matrix::Csr<V, I>* trans)
+{
+    transpose<V, I>(exec, orig, trans);
+}
+template void conj_transpose<double, int32>(Exec, const matrix::Csr<double, int32>*, matrix::Csr<double, int32>*);
+template void conj_transpose<float, int32>(Exec, const matrix::Csr<float, int32>*, matrix::Csr<float, int32>*);
+template void conj_transpose<double, int64>(Exec, const matrix::Csr<double, int64>*, matrix::Csr<double, int64>*);
+template void conj_transpose<float, int64>(Exec, const matrix::Csr<float, int64>*, matrix::Csr<float, int64>*);
 template void transpose<double, int32>(Exec, const matrix::Csr<double, int32>*, matrix::Csr<double, int32>*);
 template void transpose<float, int32>(Exec, const matrix::Csr<float, int32>*, matrix::Csr<float, int32>*);
 template void transpose<double, int64>(Exec, const matrix::Csr<double, int64>*, matrix::Csr<double, int64>*);
@@ -824,6 +834,17 @@ void set_all_statuses(Exec, uint8 id, bool fin, array<stopping_status>* stop)
 // ===================================== Jacobi ==========================================
 namespace jacobi {
 
+// real value types: conj(diag) = diag (what Jacobi::conj_transpose runs for max_block_size 1)
+template <typename V>
+void scalar_conj(Exec, const array<V>& diag, array<V>& conj_diag)
+{
+    if (diag.get_num_elems() == 0) return;
+    const cudaError_t e = cudaMemcpyAsync(conj_diag.get_data(), diag.get_const_data(), diag.get_num_elems() * sizeof(V),
+                                          cudaMemcpyDeviceToDevice, nullptr);
+    if (e != cudaSuccess) throw CudaError(__FILE__, __LINE__, "cudaMemcpyAsync", (int)e);
+}
+template void scalar_conj<double>(Exec, const array<double>&, array<double>&);
+template void scalar_conj<float>(Exec, const array<float>&, array<float>&);
 template <typename V>
 void invert_diagonal(Exec, const array<V>& diag, array<V>& inv)
 {
