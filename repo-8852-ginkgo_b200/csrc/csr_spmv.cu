@@ -378,9 +378,6 @@ __global__ void __launch_bounds__(kRowsPerCta, rowblock_min_ctas(kBatch, sizeof(
 // ---------------------------------------------------------------------------
 // merge-path kernel (single right-hand side)
 // ---------------------------------------------------------------------------
-#ifndef GKOB200_MP_MIN_CTAS
-#define GKOB200_MP_MIN_CTAS 1
-#endif
 constexpr int kMpThreads = 256;
 constexpr int kMpItems = 9;                            // merge items per thread (odd: conflict-free)
 constexpr int kMpTile = kMpThreads * kMpItems;         // merge items per CTA
@@ -405,7 +402,10 @@ __device__ __forceinline__ int64_t merge_path_search(int64_t diag, const P row_e
 }
 
 template <typename V, typename I, bool Advanced>
-__global__ void __launch_bounds__(kMpThreads, GKOB200_MP_MIN_CTAS)
+// (64 registers = 4 resident CTAs is the measured optimum on the 10 M-row power-law matrix:
+// 6 CTAs at 40 registers 1286 us, 3 CTAs at 80 registers 938 us, 4 CTAs 833 us — more tiles in
+// flight evict the gathered vector from L2)
+__global__ void __launch_bounds__(kMpThreads)
     csr_spmv_merge(int64_t n_rows, int64_t nnz, const I* __restrict__ row_ptrs, const I* __restrict__ col_idxs,
                    const V* __restrict__ values, const V* __restrict__ b, int64_t b_stride,
                    const V* __restrict__ alpha_p, const V* __restrict__ beta_p, V* __restrict__ c,
@@ -789,21 +789,12 @@ int csr_spmv_launch(cudaStream_t s, int64_t n_rows, int64_t n_cols, int64_t nnz,
         const char* f = getenv("GKOB200_MP_KEEP_FRAC");
         return f ? static_cast<float>(atof(f)) : 1.0f;
     }();
-    // resident CTAs per SM are a tuning knob through a dynamic shared-memory pad (A/B on the box)
-    static const size_t mp_pad = [] {
-        const char* e = getenv("GKOB200_MP_PAD_KB");
-        return e ? static_cast<size_t>(atoi(e)) * 1024 : size_t(0);
-    }();
-    if (mp_pad > 16 * 1024) {
-        cudaFuncSetAttribute(csr_spmv_merge<V, I, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(mp_pad));
-        cudaFuncSetAttribute(csr_spmv_merge<V, I, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(mp_pad));
-    }
     if (adv)
-        csr_spmv_merge<V, I, true><<<static_cast<unsigned>(n_tiles), kMpThreads, mp_pad, s>>>(
+        csr_spmv_merge<V, I, true><<<static_cast<unsigned>(n_tiles), kMpThreads, 0, s>>>(
             n_rows, nnz, row_ptrs, col_idxs, values, b, b_stride, alpha, beta, c, c_stride, carry_row,
             carry_val, plan, keep_frac);
     else
-        csr_spmv_merge<V, I, false><<<static_cast<unsigned>(n_tiles), kMpThreads, mp_pad, s>>>(
+        csr_spmv_merge<V, I, false><<<static_cast<unsigned>(n_tiles), kMpThreads, 0, s>>>(
             n_rows, nnz, row_ptrs, col_idxs, values, b, b_stride, alpha, beta, c, c_stride, carry_row,
             carry_val, plan, keep_frac);
     GKOB200_CHECK_LAUNCH();
