@@ -26,6 +26,7 @@
 #include "internal.h"
 #include "p2p.cuh"
 #include "spmm.cuh"
+#include "tma.cuh"
 
 namespace gkob200 {
 namespace {
@@ -159,24 +160,63 @@ constexpr int kCooTile = kCooThreads * kCooItems;
 //      range when the matrix has no long runs of empty rows) and added to c as one coalesced
 //      read-modify-write; tiles spanning more rows than fit update c directly.
 // No atomics (the reference's kernel uses atomic_add: coo_kernels.hpp.inc:54-218), deterministic.
-template <typename V, typename I, bool Advanced>
+// Bulk: the three streams of a FULL tile (16-byte aligned windows) arrive through three bulk
+// asynchronous copies (TMA, UBLKCP) issued by one thread, with an L2 prefetch of the tile one
+// resident wave ahead — the staging of the CSR row-block kernel; the products then overwrite
+// the staged values in place.  The last, partial tile (and unaligned arrays) take the
+// register-staged path (`tile0` = index of the first tile of this launch).
+template <typename V, typename I, bool Advanced, bool Bulk>
 __global__ void __launch_bounds__(kCooThreads)
     coo_spmv2(int64_t nnz, const I* __restrict__ rows, const I* __restrict__ cols, const V* __restrict__ vals,
               const V* __restrict__ b, int64_t b_stride, int64_t j, const V* __restrict__ alpha_p,
-              V* __restrict__ c, int64_t c_stride, int64_t* __restrict__ carry_row, V* __restrict__ carry_val)
+              V* __restrict__ c, int64_t c_stride, int64_t* __restrict__ carry_row, V* __restrict__ carry_val,
+              int64_t tile0, int prefetch_tiles)
 {
-    __shared__ V s_prod[kCooTile];
-    __shared__ I s_row[kCooTile];
+    extern __shared__ __align__(128) unsigned char coo_smem[];
+    V* s_prod = reinterpret_cast<V*>(coo_smem);
+    I* s_row = reinterpret_cast<I*>(coo_smem + kCooTile * sizeof(V));
+    I* s_col = s_row + kCooTile;                 // (Bulk only)
     __shared__ unsigned char s_flag[kCooTile];   // row (relative to the tile's first row) received a sum
     __shared__ V s_lead[kCooThreads];            // sum of a thread's entries before its first head
     __shared__ bool s_has[kCooThreads];          // the thread's window contains a head
+    __shared__ __align__(8) uint64_t bar;
 
     const int tid = threadIdx.x;
-    const int64_t k0 = static_cast<int64_t>(blockIdx.x) * kCooTile;
+    const int64_t tile = tile0 + blockIdx.x;
+    const int64_t k0 = tile * kCooTile;
     const int len = static_cast<int>(min(static_cast<int64_t>(kCooTile), nnz - k0));
     V alpha = V(1);
     if (Advanced) alpha = *alpha_p;
-    {
+    if (Bulk) {
+        if (tid == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&bar, kCooTile * static_cast<unsigned>(sizeof(V) + 2 * sizeof(I)));
+            bulk_g2s(s_prod, vals + k0, kCooTile * sizeof(V), &bar);
+            bulk_g2s(s_col, cols + k0, kCooTile * sizeof(I), &bar);
+            bulk_g2s(s_row, rows + k0, kCooTile * sizeof(I), &bar);
+            const int64_t ahead = k0 + static_cast<int64_t>(prefetch_tiles) * kCooTile;
+            if (prefetch_tiles > 0 && ahead + kCooTile <= nnz) {
+                bulk_prefetch_l2(vals + ahead, kCooTile * sizeof(V));
+                bulk_prefetch_l2(cols + ahead, kCooTile * sizeof(I));
+                bulk_prefetch_l2(rows + ahead, kCooTile * sizeof(I));
+            }
+        }
+        mbar_wait(&bar, 0);
+        V v[kCooItems], xv[kCooItems];
+#pragma unroll
+        for (int u = 0; u < kCooItems; ++u) {
+            const int k = tid + u * kCooThreads;
+            v[u] = s_prod[k];
+            xv[u] = ldg(b + static_cast<int64_t>(s_col[k]) * b_stride + j);
+        }
+#pragma unroll
+        for (int u = 0; u < kCooItems; ++u) {
+            const int k = tid + u * kCooThreads;
+            s_prod[k] = Advanced ? mul_rn(mul_rn(alpha, v[u]), xv[u]) : mul_rn(v[u], xv[u]);
+            s_flag[k] = 0;
+        }
+    } else {
         V v[kCooItems], xv[kCooItems];
         I col[kCooItems], row[kCooItems];
 #pragma unroll
@@ -213,17 +253,17 @@ __global__ void __launch_bounds__(kCooThreads)
     __syncthreads();   // s_prod is reused for the row results from here on
     V* s_out = s_prod;
     if (tid == 0) {
-        carry_row[2 * blockIdx.x] = carry_row[2 * blockIdx.x + 1] = -1;
-        carry_val[2 * blockIdx.x] = carry_val[2 * blockIdx.x + 1] = V(0);
+        carry_row[2 * tile] = carry_row[2 * tile + 1] = -1;
+        carry_val[2 * tile] = carry_val[2 * tile + 1] = V(0);
     }
     // a finished row sum: exported if it touches the tile's first entry, otherwise collected
     auto deliver = [&](I row, V sum, bool first_seg, bool reaches_end) {
         if (first_seg) {
-            carry_row[2 * blockIdx.x] = row;
-            carry_val[2 * blockIdx.x] = sum;
+            carry_row[2 * tile] = row;
+            carry_val[2 * tile] = sum;
         } else if (reaches_end) {
-            carry_row[2 * blockIdx.x + 1] = row;
-            carry_val[2 * blockIdx.x + 1] = sum;
+            carry_row[2 * tile + 1] = row;
+            carry_val[2 * tile + 1] = sum;
         } else if (dense) {
             s_out[row - row_first] = sum;
             s_flag[row - row_first] = 1;
@@ -316,13 +356,41 @@ int coo_spmv2_launch(cudaStream_t s, int64_t n_rows, int64_t nnz, const I* rows,
     if (!workspace || workspace_bytes < need) return GKOB200_EWORKSPACE;
     int64_t* carry_row = reinterpret_cast<int64_t*>(workspace);
     V* carry_val = reinterpret_cast<V*>(carry_row + 2 * n_tiles);
+    // full tiles of 16-byte aligned arrays are staged by bulk copies (GKOB200_COO_BULK=0: A/B)
+    static const bool bulk_on = [] {
+        const char* e = getenv("GKOB200_COO_BULK");
+        return !(e && e[0] == '0');
+    }();
+    const bool aligned = reinterpret_cast<uintptr_t>(rows) % 16 == 0 && reinterpret_cast<uintptr_t>(cols) % 16 == 0 &&
+                         reinterpret_cast<uintptr_t>(vals) % 16 == 0;
+    const int64_t n_bulk = (bulk_on && aligned) ? nnz / kCooTile : 0;
+    const size_t smem_plain = kCooTile * (sizeof(V) + sizeof(I)), smem_bulk = kCooTile * (sizeof(V) + 2 * sizeof(I));
+    const int pf = sm_count() * static_cast<int>((227 * 1024) / (smem_bulk + 6 * 1024));
+    if (n_bulk > 0 && smem_bulk + 5 * 1024 > 48 * 1024) {   // 64-bit indices: 54 KB of staging
+        static const cudaError_t attr = [&] {
+            cudaError_t e = cudaFuncSetAttribute(coo_spmv2<V, I, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 static_cast<int>(smem_bulk));
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(coo_spmv2<V, I, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem_bulk));
+            return e;
+        }();
+        if (attr != cudaSuccess) return static_cast<int>(attr);
+    }
     for (int64_t j = 0; j < nrhs; ++j) {
-        if (alpha)
-            coo_spmv2<V, I, true><<<static_cast<unsigned>(n_tiles), kCooThreads, 0, s>>>(
-                nnz, rows, cols, vals, b, b_stride, j, alpha, c, c_stride, carry_row, carry_val);
-        else
-            coo_spmv2<V, I, false><<<static_cast<unsigned>(n_tiles), kCooThreads, 0, s>>>(
-                nnz, rows, cols, vals, b, b_stride, j, alpha, c, c_stride, carry_row, carry_val);
+#define GKOB200_COO(ADV)                                                                                           \
+    if (n_bulk > 0)                                                                                                \
+        coo_spmv2<V, I, ADV, true><<<static_cast<unsigned>(n_bulk), kCooThreads, smem_bulk, s>>>(                   \
+            nnz, rows, cols, vals, b, b_stride, j, alpha, c, c_stride, carry_row, carry_val, int64_t(0), pf);       \
+    if (n_tiles > n_bulk)                                                                                          \
+        coo_spmv2<V, I, ADV, false><<<static_cast<unsigned>(n_tiles - n_bulk), kCooThreads, smem_plain, s>>>(       \
+            nnz, rows, cols, vals, b, b_stride, j, alpha, c, c_stride, carry_row, carry_val, n_bulk, 0)
+        if (alpha) {
+            GKOB200_COO(true);
+        } else {
+            GKOB200_COO(false);
+        }
+#undef GKOB200_COO
         GKOB200_CHECK_LAUNCH();
         coo_fixup<V><<<static_cast<unsigned>(ceildiv(2 * n_tiles, 256)), 256, 0, s>>>(2 * n_tiles, carry_row, carry_val, c,
                                                                                    c_stride, j);

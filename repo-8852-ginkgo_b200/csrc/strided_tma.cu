@@ -340,6 +340,17 @@ bool ell_tensor_map(const T* base, int64_t stride, int64_t width, CUtensorMap* o
     return true;
 }
 
+// gathers kept in flight per thread for rows wider than 18 entries: 14 (like the CSR row-block
+// kernel on the 27-pt stencil) or 9; GKOB200_STRIDED_BATCH=9 keeps the round-1 setting (A/B)
+inline bool strided_batch14()
+{
+    static const bool v = [] {
+        const char* e = getenv("GKOB200_STRIDED_BATCH");
+        return !(e && atoi(e) == 9);
+    }();
+    return v;
+}
+
 inline int resident_ctas(size_t smem)
 {
     int r = static_cast<int>((227 * 1024) / (smem + 1024));
@@ -381,7 +392,10 @@ int sellp_spmv_tma_launch(cudaStream_t s, int64_t n_rows, int64_t slice_size, co
                                        alpha, beta, c, c_stride, cap, fu, pf, total);                              \
     }
     const bool wide = max_slice_len > 8;
-    if (wide) {
+    if (max_slice_len > 18 && strided_batch14()) {
+        if (adv && fused) GKOB200_SP(true, true, 14) else if (adv) GKOB200_SP(true, false, 14)
+        else if (fused) GKOB200_SP(false, true, 14) else GKOB200_SP(false, false, 14)
+    } else if (wide) {
         if (adv && fused) GKOB200_SP(true, true, 9) else if (adv) GKOB200_SP(true, false, 9)
         else if (fused) GKOB200_SP(false, true, 9) else GKOB200_SP(false, false, 9)
     } else {
@@ -433,7 +447,10 @@ int ell_spmv_tma_launch(cudaStream_t s, int64_t n_rows, int64_t stride, int64_t 
         kern<<<grid, kRows, smem, s>>>(n_rows, static_cast<int>(width), tm_val, tm_col, b, pitch, alpha, beta, c,   \
                                        c_stride, fu, pf);                                                          \
     }
-        if (width > 8) {
+        if (width > 18 && strided_batch14()) {
+            if (adv && fused) GKOB200_EL2(true, true, 14) else if (adv) GKOB200_EL2(true, false, 14)
+            else if (fused) GKOB200_EL2(false, true, 14) else GKOB200_EL2(false, false, 14)
+        } else if (width > 8) {
             if (adv && fused) GKOB200_EL2(true, true, 9) else if (adv) GKOB200_EL2(true, false, 9)
             else if (fused) GKOB200_EL2(false, true, 9) else GKOB200_EL2(false, false, 9)
         } else {
