@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(kRowsPerCta)
                       int64_t c_stride, int cap, SpmvFusion<V> fu)
 {
     if (Fused && fu.skip && *fu.skip) return;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     V* s_val = reinterpret_cast<V*>(smem_raw);
     I* s_col = reinterpret_cast<I*>(smem_raw + align16(static_cast<size_t>(padded_size(cap)) * sizeof(V)));
     __shared__ I s_ptr[kRowsPerCta + 1];
@@ -401,7 +401,7 @@ __device__ __forceinline__ int64_t merge_path_search(int64_t diag, const P row_e
     return lo;
 }
 
-template <typename V, typename I, bool Advanced>
+template <typename V, typename I, bool Advanced, bool Bulk>
 // (64 registers = 4 resident CTAs is the measured optimum on the 10 M-row power-law matrix:
 // 6 CTAs at 40 registers 1286 us, 3 CTAs at 80 registers 938 us, 4 CTAs 833 us — more tiles in
 // flight evict the gathered vector from L2)
@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(kMpThreads)
                    const V* __restrict__ values, const V* __restrict__ b, int64_t b_stride,
                    const V* __restrict__ alpha_p, const V* __restrict__ beta_p, V* __restrict__ c,
                    int64_t c_stride, int64_t* __restrict__ carry_row, V* __restrict__ carry_val,
-                   const int64_t* __restrict__ plan, float keep_frac)
+                   const int64_t* __restrict__ plan, float keep_frac, int prefetch_tiles)
 {
     // The merge path only cuts the matrix into tiles of equal rows + entries; inside a tile
     // the row sums are a segmented reduction over the tile's products:
@@ -419,7 +419,10 @@ __global__ void __launch_bounds__(kMpThreads)
     // thread t owns the kMpItems consecutive entries [t*kMpItems, ...): it loads them and their
     // heads with independent shared-memory reads and reduces them in registers (no search, no
     // dependent shared-memory chain); rows that span threads are stitched in thread order.
-    __shared__ V s_prod[kMpTile];
+    constexpr int VA = 16 / sizeof(V), IA = 16 / sizeof(I);
+    __shared__ __align__(128) V s_prod[kMpTile + VA];      // (Bulk: the staged values first)
+    __shared__ __align__(128) I s_cstage[Bulk ? kMpTile + IA : 1];
+    __shared__ __align__(8) uint64_t bar;
     __shared__ int s_head[kMpTile];
     __shared__ int64_t s_range[4];
     __shared__ V s_lead[kMpThreads];      // sum of a thread's entries before its first head
@@ -442,6 +445,7 @@ __global__ void __launch_bounds__(kMpThreads)
     }
 #pragma unroll
     for (int u = 0; u < kMpItems; ++u) s_head[tid + u * kMpThreads] = -1;
+    if (Bulk && tid == 0) mbar_init(&bar, 1);
     __syncthreads();
     const int64_t r_begin = s_range[0], k_begin = s_range[1];
     const int64_t r_end = s_range[2], k_end = s_range[3];
@@ -459,12 +463,52 @@ __global__ void __launch_bounds__(kMpThreads)
         const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last(keep_frac);
         V v[kMpItems], xv[kMpItems];
         I col[kMpItems];
+        if (Bulk) {
+            // The tile's (col, val) ranges are contiguous: the 16-byte aligned interior arrives through
+            // two bulk asynchronous copies (TMA) issued by one thread — with an L2 prefetch of the
+            // tile one resident wave ahead when the plan tells where that tile starts — and the
+            // (< 16 bytes) tails through plain loads; like the row-block kernel.
+            const int64_t vb = k_begin & ~static_cast<int64_t>(VA - 1), vf = k_end & ~static_cast<int64_t>(VA - 1);
+            const int64_t cb = k_begin & ~static_cast<int64_t>(IA - 1), cf = k_end & ~static_cast<int64_t>(IA - 1);
+            if (tid == 0) {
+                const unsigned vbytes = vf > vb ? static_cast<unsigned>((vf - vb) * sizeof(V)) : 0u;
+                const unsigned cbytes = cf > cb ? static_cast<unsigned>((cf - cb) * sizeof(I)) : 0u;
+                mbar_expect_tx(&bar, vbytes + cbytes);
+                if (vbytes) bulk_g2s(s_prod, values + vb, vbytes, &bar);
+                if (cbytes) bulk_g2s(s_cstage, col_idxs + cb, cbytes, &bar);
+                if (plan && prefetch_tiles > 0 && static_cast<int64_t>(blockIdx.x) + prefetch_tiles < gridDim.x) {
+                    const int64_t dp = min((static_cast<int64_t>(blockIdx.x) + prefetch_tiles) * kMpTile, total);
+                    const int64_t kp = (dp - plan[blockIdx.x + prefetch_tiles]) & ~static_cast<int64_t>(3);
+                    if (kp + kMpTile <= nnz) {
+                        bulk_prefetch_l2(values + kp, kMpTile * sizeof(V));
+                        bulk_prefetch_l2(col_idxs + kp, kMpTile * sizeof(I));
+                    }
+                }
+            }
+            {
+                const int64_t vt = vf > vb ? vf : vb;
+                if (tid < VA && vt + tid < k_end) s_prod[vt + tid - vb] = values[vt + tid];
+                const int64_t ct = cf > cb ? cf : cb;
+                if (tid >= 32 && tid < 32 + IA && ct + (tid - 32) < k_end) s_cstage[ct + (tid - 32) - cb] = col_idxs[ct + (tid - 32)];
+            }
+            mbar_wait(&bar, 0);
+            __syncthreads();   // tails visible
+            const int dv = static_cast<int>(k_begin - vb), dc = static_cast<int>(k_begin - cb);
 #pragma unroll
-        for (int u = 0; u < kMpItems; ++u) {
-            const int k = tid + u * kMpThreads;
-            const bool in = k < n_tile_nnz;
-            col[u] = in ? ld_hint(col_idxs + k_begin + k, pol_stream) : I(0);
-            v[u] = in ? ld_hint(values + k_begin + k, pol_stream) : V(0);
+            for (int u = 0; u < kMpItems; ++u) {
+                const int k = tid + u * kMpThreads;
+                const bool in = k < n_tile_nnz;
+                col[u] = in ? s_cstage[dc + k] : I(0);
+                v[u] = in ? s_prod[dv + k] : V(0);
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < kMpItems; ++u) {
+                const int k = tid + u * kMpThreads;
+                const bool in = k < n_tile_nnz;
+                col[u] = in ? ld_hint(col_idxs + k_begin + k, pol_stream) : I(0);
+                v[u] = in ? ld_hint(values + k_begin + k, pol_stream) : V(0);
+            }
         }
 #pragma unroll
         for (int u = 0; u < kMpItems; ++u) xv[u] = ld_hint(b + static_cast<int64_t>(col[u]) * b_stride, pol_keep);
@@ -477,6 +521,7 @@ __global__ void __launch_bounds__(kMpThreads)
                                             : n_tile_nnz;
             if (start < end) s_head[start] = r;
         }
+        if (Bulk) __syncthreads();   // every staged value is in a register before products overwrite the buffer
 #pragma unroll
         for (int u = 0; u < kMpItems; ++u) {
             const int k = tid + u * kMpThreads;
@@ -789,14 +834,30 @@ int csr_spmv_launch(cudaStream_t s, int64_t n_rows, int64_t n_cols, int64_t nnz,
         const char* f = getenv("GKOB200_MP_KEEP_FRAC");
         return f ? static_cast<float>(atof(f)) : 1.0f;
     }();
-    if (adv)
-        csr_spmv_merge<V, I, true><<<static_cast<unsigned>(n_tiles), kMpThreads, 0, s>>>(
-            n_rows, nnz, row_ptrs, col_idxs, values, b, b_stride, alpha, beta, c, c_stride, carry_row,
-            carry_val, plan, keep_frac);
-    else
-        csr_spmv_merge<V, I, false><<<static_cast<unsigned>(n_tiles), kMpThreads, 0, s>>>(
-            n_rows, nnz, row_ptrs, col_idxs, values, b, b_stride, alpha, beta, c, c_stride, carry_row,
-            carry_val, plan, keep_frac);
+    // bulk-async staging of the tile's (col, val) ranges needs 16-byte aligned arrays
+    // (GKOB200_MP_BULK=0: register-staged loads, for A/B on the box)
+    static const bool mp_bulk = [] {
+        const char* e = getenv("GKOB200_MP_BULK");
+        return !(e && e[0] == '0');
+    }();
+    const bool bulk = mp_bulk && sizeof(I) == 4 && reinterpret_cast<uintptr_t>(values) % 16 == 0 &&
+                      reinterpret_cast<uintptr_t>(col_idxs) % 16 == 0;   // (64-bit indices: the staging would not fit 48 KB)
+    const int mp_pf = sm_count() * 4;
+#define GKOB200_MP(ADV, BULK)                                                                              \
+    csr_spmv_merge<V, I, ADV, BULK><<<static_cast<unsigned>(n_tiles), kMpThreads, 0, s>>>(                 \
+        n_rows, nnz, row_ptrs, col_idxs, values, b, b_stride, alpha, beta, c, c_stride, carry_row, carry_val, \
+        plan, keep_frac, mp_pf)
+    if (bulk) {
+        if constexpr (sizeof(I) == 4) {
+            if (adv) GKOB200_MP(true, true);
+            else GKOB200_MP(false, true);
+        }
+    } else if (adv) {
+        GKOB200_MP(true, false);
+    } else {
+        GKOB200_MP(false, false);
+    }
+#undef GKOB200_MP
     GKOB200_CHECK_LAUNCH();
     csr_spmv_merge_fixup<V><<<static_cast<unsigned>(ceildiv(n_tiles, 8)), 256, 0, s>>>(
         static_cast<int>(n_tiles), carry_row, carry_val, n_rows, c, c_stride);
