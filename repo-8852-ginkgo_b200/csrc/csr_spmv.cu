@@ -381,6 +381,16 @@ __global__ void __launch_bounds__(kRowsPerCta, rowblock_min_ctas(kBatch, sizeof(
 constexpr int kMpThreads = 256;
 constexpr int kMpItems = 9;                            // merge items per thread (odd: conflict-free)
 constexpr int kMpTile = kMpThreads * kMpItems;         // merge items per CTA
+static int mp_threads()
+{
+    static const int t = [] {
+        const char* e = getenv("GKOB200_MP_THREADS");
+        const int v = e ? atoi(e) : 128;
+        return v == 64 || v == 256 ? v : 128;
+    }();
+    return t;
+}
+static int mp_tile() { return mp_threads() * kMpItems; }
 
 // Merge-path diagonal search: how many of the first `diag` merge items are row
 // ends.  List A = row end offsets row_ptrs[1..n], list B = 0..nnz-1; a row end is
@@ -401,243 +411,197 @@ __device__ __forceinline__ int64_t merge_path_search(int64_t diag, const P row_e
     return lo;
 }
 
-template <typename V, typename I, bool Advanced, bool Bulk>
-// (64 registers = 4 resident CTAs is the measured optimum on the 10 M-row power-law matrix:
-// 6 CTAs at 40 registers 1286 us, 3 CTAs at 80 registers 938 us, 4 CTAs 833 us — more tiles in
-// flight evict the gathered vector from L2)
-__global__ void __launch_bounds__(kMpThreads)
+// One tile = kMpTile consecutive merge items (rows + entries), cut by the merge path: tiles are
+// equal amounts of work whatever the row lengths.  Inside a tile:
+//   1. every thread issues its kMpItems (col, val) loads, the loads of the row boundaries it will
+//      stage, then its kMpItems gathers — all independent, all in flight together (the gathers of
+//      a skewed matrix are random 32-byte sectors: what has to be hidden is latency);
+//   2. products and tile-relative row starts go to shared memory; ONE barrier;
+//   3. one thread per tile row walks that row's products front to back (storage order: a row that
+//      lies inside one tile gets exactly the reference's sequential sum) and stores the result;
+//      a row with more than kMpLongRow entries in the tile is summed by its whole warp instead
+//      (lane-strided partial sums + shuffle tree — a fixed association, deterministic);
+//   4. the row left open at the end of the tile leaves a carry for the fix-up kernel.
+// With a plan (tile split rows computed once per matrix) there is no search and no second
+// barrier.  History (profiles/r02_merge_source_phases.txt): the previous kernel flagged row
+// heads per entry, reduced kMpItems consecutive products per thread and stitched the pieces in
+// thread order — 8 barriers per tile, 37 % of all warp time in the stitch and the barrier
+// behind it; 833 us on the 10 M-row power-law matrix against 721 us for this one.
+// 4 resident CTAs (64 registers) is the measured optimum at 10 M rows: 3 CTAs 785 us, 5 CTAs
+// (48 registers) 794 us, 6 CTAs (40 registers, spills) 1128 us.
+constexpr int kMpLongRow = 48;
+
+template <typename V, typename I, bool Advanced, int kMpThreads>
+__global__ void __launch_bounds__(kMpThreads, 1024 / kMpThreads)
     csr_spmv_merge(int64_t n_rows, int64_t nnz, const I* __restrict__ row_ptrs, const I* __restrict__ col_idxs,
                    const V* __restrict__ values, const V* __restrict__ b, int64_t b_stride,
                    const V* __restrict__ alpha_p, const V* __restrict__ beta_p, V* __restrict__ c,
                    int64_t c_stride, int64_t* __restrict__ carry_row, V* __restrict__ carry_val,
-                   const int64_t* __restrict__ plan, float keep_frac, int prefetch_tiles)
+                   const int64_t* __restrict__ plan, int prefetch_tiles)
 {
-    // The merge path only cuts the matrix into tiles of equal rows + entries; inside a tile
-    // the row sums are a segmented reduction over the tile's products:
-    //   s_prod[k]  product of entry k (coalesced loads, gathers batched per thread)
-    //   s_head[k]  tile row that STARTS at entry k, or -1
-    // thread t owns the kMpItems consecutive entries [t*kMpItems, ...): it loads them and their
-    // heads with independent shared-memory reads and reduces them in registers (no search, no
-    // dependent shared-memory chain); rows that span threads are stitched in thread order.
-    constexpr int VA = 16 / sizeof(V), IA = 16 / sizeof(I);
-    __shared__ __align__(128) V s_prod[kMpTile + VA];      // (Bulk: the staged values first)
-    __shared__ __align__(128) I s_cstage[Bulk ? kMpTile + IA : 1];
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ int s_head[kMpTile];
-    __shared__ int64_t s_range[4];
-    __shared__ V s_lead[kMpThreads];      // sum of a thread's entries before its first head
-    __shared__ V s_trail[kMpThreads];     // sum of its entries from its last head on
-    __shared__ int s_last[kMpThreads];    // tile row of its last head, -1: no head in the window
+    constexpr int kMpTile = kMpThreads * kMpItems;
+    __shared__ __align__(16) V s_prod[kMpTile];
+    __shared__ int s_start[kMpTile + 2];   // [r]: first product of tile row r; [n_tile_rows + 1] = n_tile_nnz
+    __shared__ int64_t s_range[2];
 
     const int tid = threadIdx.x;
     const int64_t total = n_rows + nnz;
     const int64_t diag0 = min(static_cast<int64_t>(blockIdx.x) * kMpTile, total);
     const int64_t diag1 = min(diag0 + kMpTile, total);
     const I* row_end = row_ptrs + 1;
-    if (tid < 2) {
-        const int64_t d = tid == 0 ? diag0 : diag1;
-        // planned: the tile's split point was computed once per matrix (gkob200_csr_merge_plan_*),
-        // otherwise two binary searches over row_ptrs per CTA and per call (24 dependent loads
-        // at 10^7 rows)
-        const int64_t r = plan ? plan[blockIdx.x + tid] : merge_path_search<I>(d, row_end, n_rows, nnz);
-        s_range[tid * 2] = r;
-        s_range[tid * 2 + 1] = d - r;
+    int64_t r_begin, r_end, pf_row = -1;
+    if (plan) {
+        // same two words for the whole CTA: one broadcast request, no barrier
+        r_begin = plan[blockIdx.x];
+        r_end = plan[blockIdx.x + 1];
+        if (tid == 0 && prefetch_tiles > 0 && blockIdx.x + prefetch_tiles < gridDim.x) pf_row = plan[blockIdx.x + prefetch_tiles];
+    } else {
+        if (tid < 2) s_range[tid] = merge_path_search<I>(tid == 0 ? diag0 : diag1, row_end, n_rows, nnz);
+        __syncthreads();
+        r_begin = s_range[0];
+        r_end = s_range[1];
     }
-#pragma unroll
-    for (int u = 0; u < kMpItems; ++u) s_head[tid + u * kMpThreads] = -1;
-    if (Bulk && tid == 0) mbar_init(&bar, 1);
-    __syncthreads();
-    const int64_t r_begin = s_range[0], k_begin = s_range[1];
-    const int64_t r_end = s_range[2], k_end = s_range[3];
-    const int n_tile_rows = static_cast<int>(r_end - r_begin);   // rows that END in this tile
-    const int n_tile_nnz = static_cast<int>(k_end - k_begin);
+    const int64_t k_begin = diag0 - r_begin;
+    const int n_tile_rows = static_cast<int>(r_end - r_begin);                 // rows that END in this tile
+    const int n_tile_nnz = static_cast<int>((diag1 - r_end) - k_begin);
+    const I* tile_cols = col_idxs + k_begin;
+    const V* tile_vals = values + k_begin;
+    const I* tile_row_end = row_end + r_begin - 1;   // [r]: end of tile row r-1 = start of tile row r (r >= 1)
     V alpha = V(1);
     if (Advanced) alpha = *alpha_p;
-
-    // coalesced staging of the products.  Every thread first issues all its (col, val) loads,
-    // then all its gathers, then forms the products: up to kMpItems independent requests in
-    // flight per thread (the gathers of a skewed matrix are random 32-byte sectors — latency,
-    // not bandwidth, is what has to be hidden).  Streams are marked evict_first, the gathered
-    // vector evict_last (see tma.cuh).
     {
-        const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last(keep_frac);
         V v[kMpItems], xv[kMpItems];
         I col[kMpItems];
-        if (Bulk) {
-            // The tile's (col, val) ranges are contiguous: the 16-byte aligned interior arrives through
-            // two bulk asynchronous copies (TMA) issued by one thread — with an L2 prefetch of the
-            // tile one resident wave ahead when the plan tells where that tile starts — and the
-            // (< 16 bytes) tails through plain loads; like the row-block kernel.
-            const int64_t vb = k_begin & ~static_cast<int64_t>(VA - 1), vf = k_end & ~static_cast<int64_t>(VA - 1);
-            const int64_t cb = k_begin & ~static_cast<int64_t>(IA - 1), cf = k_end & ~static_cast<int64_t>(IA - 1);
-            if (tid == 0) {
-                const unsigned vbytes = vf > vb ? static_cast<unsigned>((vf - vb) * sizeof(V)) : 0u;
-                const unsigned cbytes = cf > cb ? static_cast<unsigned>((cf - cb) * sizeof(I)) : 0u;
-                mbar_expect_tx(&bar, vbytes + cbytes);
-                if (vbytes) bulk_g2s(s_prod, values + vb, vbytes, &bar);
-                if (cbytes) bulk_g2s(s_cstage, col_idxs + cb, cbytes, &bar);
-                if (plan && prefetch_tiles > 0 && static_cast<int64_t>(blockIdx.x) + prefetch_tiles < gridDim.x) {
-                    const int64_t dp = min((static_cast<int64_t>(blockIdx.x) + prefetch_tiles) * kMpTile, total);
-                    const int64_t kp = (dp - plan[blockIdx.x + prefetch_tiles]) & ~static_cast<int64_t>(3);
-                    if (kp + kMpTile <= nnz) {
-                        bulk_prefetch_l2(values + kp, kMpTile * sizeof(V));
-                        bulk_prefetch_l2(col_idxs + kp, kMpTile * sizeof(I));
-                    }
-                }
-            }
-            {
-                const int64_t vt = vf > vb ? vf : vb;
-                if (tid < VA && vt + tid < k_end) s_prod[vt + tid - vb] = values[vt + tid];
-                const int64_t ct = cf > cb ? cf : cb;
-                if (tid >= 32 && tid < 32 + IA && ct + (tid - 32) < k_end) s_cstage[ct + (tid - 32) - cb] = col_idxs[ct + (tid - 32)];
-            }
-            mbar_wait(&bar, 0);
-            __syncthreads();   // tails visible
-            const int dv = static_cast<int>(k_begin - vb), dc = static_cast<int>(k_begin - cb);
-#pragma unroll
-            for (int u = 0; u < kMpItems; ++u) {
-                const int k = tid + u * kMpThreads;
-                const bool in = k < n_tile_nnz;
-                col[u] = in ? s_cstage[dc + k] : I(0);
-                v[u] = in ? s_prod[dv + k] : V(0);
-            }
-        } else {
-#pragma unroll
-            for (int u = 0; u < kMpItems; ++u) {
-                const int k = tid + u * kMpThreads;
-                const bool in = k < n_tile_nnz;
-                col[u] = in ? ld_hint(col_idxs + k_begin + k, pol_stream) : I(0);
-                v[u] = in ? ld_hint(values + k_begin + k, pol_stream) : V(0);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < kMpItems; ++u) xv[u] = ld_hint(b + static_cast<int64_t>(col[u]) * b_stride, pol_keep);
-        // heads: tile row r (1 <= r <= n_tile_rows; r == n_tile_rows is the row left open at the
-        // end of the tile) starts where row r-1 ends, if it has an entry in this tile.  Tile
-        // row 0 is open when the tile starts (its head, if any, lies in an earlier tile).
-        for (int r = tid + 1; r <= n_tile_rows; r += kMpThreads) {
-            const int start = static_cast<int>(static_cast<int64_t>(row_end[r_begin + r - 1]) - k_begin);
-            const int end = r < n_tile_rows ? static_cast<int>(static_cast<int64_t>(row_end[r_begin + r]) - k_begin)
-                                            : n_tile_nnz;
-            if (start < end) s_head[start] = r;
-        }
-        if (Bulk) __syncthreads();   // every staged value is in a register before products overwrite the buffer
 #pragma unroll
         for (int u = 0; u < kMpItems; ++u) {
             const int k = tid + u * kMpThreads;
-            // entries past the end of the tile count as zeros of the open row
-            s_prod[k] = k < n_tile_nnz ? (Advanced ? mul_rn(mul_rn(alpha, v[u]), xv[u]) : mul_rn(v[u], xv[u])) : V(0);
+            const bool in = k < n_tile_nnz;
+            col[u] = in ? __ldcs(tile_cols + k) : I(0);
+            v[u] = in ? __ldcs(tile_vals + k) : V(0);
+        }
+        // row boundaries of the first kMpThreads tile rows: requested before the gathers queue up
+        I first_end = I(0);
+        if (tid >= 1 && tid <= n_tile_rows) first_end = __ldcs(tile_row_end + tid);
+#pragma unroll
+        for (int u = 0; u < kMpItems; ++u) xv[u] = __ldg(b + static_cast<int64_t>(col[u]) * b_stride);
+        if (pf_row >= 0) {
+            // L2 prefetch of the (col, val) ranges of the tile one resident wave ahead: its CTA then
+            // starts its gathers an L2 hit, not a DRAM access, after it was launched
+            const int64_t kp = (min((static_cast<int64_t>(blockIdx.x) + prefetch_tiles) * kMpTile, total) - pf_row) &
+                               ~static_cast<int64_t>(3);
+            if (kp + kMpTile <= nnz) {
+                bulk_prefetch_l2(values + kp, kMpTile * sizeof(V));
+                bulk_prefetch_l2(col_idxs + kp, kMpTile * sizeof(I));
+            }
+        }
+        // tile row r (r == n_tile_rows: the row left open at the end of the tile) starts where row
+        // r-1 ends; tile row 0 is open when the tile starts
+        s_start[tid] = tid == 0 ? 0
+                                : (tid <= n_tile_rows ? static_cast<int>(static_cast<int64_t>(first_end) - k_begin) : n_tile_nnz);
+        for (int r = tid + kMpThreads; r <= n_tile_rows + 1; r += kMpThreads)
+            s_start[r] = r <= n_tile_rows ? static_cast<int>(static_cast<int64_t>(__ldcs(tile_row_end + r)) - k_begin) : n_tile_nnz;
+#pragma unroll
+        for (int u = 0; u < kMpItems; ++u) {
+            const int k = tid + u * kMpThreads;
+            if (k < n_tile_nnz) s_prod[k] = Advanced ? mul_rn(mul_rn(alpha, v[u]), xv[u]) : mul_rn(v[u], xv[u]);
         }
     }
     __syncthreads();
 
-    // per-thread segmented reduction in registers
-    V p[kMpItems];
-    int h[kMpItems];
-#pragma unroll
-    for (int u = 0; u < kMpItems; ++u) {
-        p[u] = s_prod[tid * kMpItems + u];
-        h[u] = s_head[tid * kMpItems + u];
-    }
-    __syncthreads();   // s_prod is reused for the row results from here on
-    V* s_out = s_prod;
-    for (int r = tid; r < n_tile_rows; r += kMpThreads) s_out[r] = V(0);   // empty rows, and rows stitched below
-    __syncthreads();
-    V lead = V(0), acc = V(0);
-    int cur = -1;   // tile row being accumulated; -1: the row open at the start of the window
-#pragma unroll
-    for (int u = 0; u < kMpItems; ++u) {
-        if (h[u] >= 0) {
-            // a row starts here: what was accumulated so far is complete for `cur` unless cur
-            // is the window's leading segment (that one is stitched with earlier threads)
-            if (cur < 0)
-                lead = acc;
-            else
-                s_out[cur] = acc;   // sole contributor: head and next head both in this window
-            cur = h[u];
-            acc = p[u];
-        } else {
-            acc = add_rn(acc, p[u]);
+    const int lane = tid & 31;
+    for (int base = 0; base <= n_tile_rows; base += kMpThreads) {   // warp-uniform trip count
+        const int r = base + tid;
+        const bool valid = r <= n_tile_rows;
+        const int start = valid ? s_start[r] : 0, end = valid ? s_start[r + 1] : 0;
+        const bool is_long = end - start > kMpLongRow;
+        V acc = V(0);
+        if (!is_long) {
+            int k = start;
+            for (; k + 4 <= end; k += 4) {
+                const V a0 = s_prod[k], a1 = s_prod[k + 1], a2 = s_prod[k + 2], a3 = s_prod[k + 3];
+                acc = add_rn(add_rn(add_rn(add_rn(acc, a0), a1), a2), a3);
+            }
+            for (; k < end; ++k) acc = add_rn(acc, s_prod[k]);
         }
-    }
-    if (cur < 0) {
-        lead = acc;
-        acc = V(0);
-    }
-    s_lead[tid] = lead;
-    s_trail[tid] = acc;
-    s_last[tid] = cur;
-    if (tid == 0) {
-        // default: no carry (the open row has no entry in this tile yet); overwritten below
-        carry_row[blockIdx.x] = -1;
-        carry_val[blockIdx.x] = V(0);
-    }
-    __syncthreads();
-    // Stitch in thread order (left-to-right association).  The thread holding the last head of
-    // a row adds its trailing sum and the leading sums of the following threads up to and
-    // including the next thread that has a head; thread 0 does the same for the row that was
-    // open when the tile started.
-    {
-        auto run_from = [&](V run, int t) {
-            // add lead[t], lead[t+1], ... until (and including) the first thread with a head
-            while (t < kMpThreads) {
-                run = add_rn(run, s_lead[t]);
-                if (s_last[t] >= 0) break;
-                ++t;
-            }
-            return run;
-        };
-        auto deliver = [&](int row, V run) {
-            if (row < n_tile_rows) {
-                s_out[row] = run;
-            } else {
-                // the row continues into the next tile: per-CTA carry
-                carry_row[blockIdx.x] = r_begin + row;
-                carry_val[blockIdx.x] = run;
-            }
-        };
-        if (tid == 0) deliver(0, run_from(V(0), 0));
-        if (cur >= 0) deliver(cur, run_from(acc, tid + 1));
-    }
-    __syncthreads();
-    for (int r = tid; r < n_tile_rows; r += kMpThreads) {
-        const int64_t row = r_begin + r;
-        // beta*c is applied exactly once, by the tile in which the row ends
-        c[row * c_stride] = Advanced ? add_rn(mul_rn(c[row * c_stride], *beta_p), s_out[r]) : s_out[r];
+        for (unsigned m = __ballot_sync(0xffffffffu, is_long); m; m &= m - 1) {
+            const int src = __ffs(m) - 1;
+            const int ls = __shfl_sync(0xffffffffu, start, src), le = __shfl_sync(0xffffffffu, end, src);
+            V part = V(0);
+            for (int k = ls + lane; k < le; k += 32) part = add_rn(part, s_prod[k]);
+            part = __shfl_sync(0xffffffffu, warp_sum(part), 0);   // (the tree leaves the total in lane 0)
+            if (lane == src) acc = part;
+        }
+        if (!valid) continue;
+        if (r < n_tile_rows) {
+            const int64_t row = r_begin + r;
+            // beta*c is applied exactly once, by the tile in which the row ends
+            // (streaming store: the result must not push the gathered vector out of L2)
+            __stcs(c + row * c_stride, Advanced ? add_rn(mul_rn(c[row * c_stride], *beta_p), acc) : acc);
+        } else {
+            // the row continues into the next tile: per-CTA carry (-1: no entry of it in this tile)
+            carry_row[blockIdx.x] = end > start ? r_begin + r : int64_t(-1);
+            carry_val[blockIdx.x] = acc;
+        }
     }
 }
 
 // split row of every tile diagonal, computed once per matrix
 template <typename I>
 __global__ void csr_merge_plan(int64_t n_tiles, int64_t n_rows, int64_t nnz, const I* __restrict__ row_ptrs,
-                               int64_t* __restrict__ plan)
+                               int64_t* __restrict__ plan, int tile)
 {
     const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (t > n_tiles) return;
     const int64_t total = n_rows + nnz;
-    const int64_t d = min(t * kMpTile, total);
+    const int64_t d = min(t * tile, total);
     plan[t] = merge_path_search<I>(d, row_ptrs + 1, n_rows, nnz);
 }
 
-// Fix-up: tile carries belonging to the same row are consecutive; one WARP per tile, the warp
-// of the first tile of each run adds the run (lane-strided partial sums, then a shuffle tree: a
-// fixed association for a given run length, so the result is deterministic) and applies it to
-// c.  A row of 10^5 entries spans ~350 tiles: a single thread walking them would put ~350
-// dependent loads on the critical path of every SpMV.
+// Fix-up: tile carries belonging to the same row are consecutive.  One LANE per tile, a warp
+// owns a window of 32 tiles: the carries of the window arrive in three coalesced, independent
+// loads, runs of equal rows are added by a segmented shuffle scan, and the lane at the start of
+// a run applies the sum to c.  A run that leaves the window (a row of 10^5 entries spans ~90
+// tiles) is continued by the whole warp, 32 tiles per step.  Fixed association for a given tile
+// layout: deterministic.  (One warp per tile, the previous scheme, was a chain of 4-5 dependent
+// memory latencies for each of ~10^5 warps: 24 us at 10 M rows.)
 template <typename V>
 __global__ void __launch_bounds__(256) csr_spmv_merge_fixup(int n_tiles, const int64_t* __restrict__ carry_row,
                                                             const V* __restrict__ carry_val, int64_t n_rows,
                                                             V* __restrict__ c, int64_t c_stride)
 {
-    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (t >= n_tiles) return;
-    const int64_t row = carry_row[t];
-    if (row < 0 || row >= n_rows) return;
-    if (t > 0 && carry_row[t - 1] == row) return;
-    V run = V(0);
-    for (int u = t + lane; u < n_tiles && carry_row[u] == row; u += 32) run = add_rn(run, carry_val[u]);
-    run = warp_sum(run);
-    if (lane == 0) c[row * c_stride] = add_rn(run, c[row * c_stride]);
+    constexpr unsigned kFull = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
+    if (base >= n_tiles) return;   // warp-uniform
+    const int t = base + lane;
+    int64_t row = t < n_tiles ? carry_row[t] : int64_t(-1);
+    int64_t before = lane == 0 && base > 0 ? carry_row[base - 1] : int64_t(-1);
+    V sum = t < n_tiles ? carry_val[t] : V(0);
+    int64_t beyond = base + 32 + lane < n_tiles ? carry_row[base + 32 + lane] : int64_t(-1);
+    if (row >= n_rows) row = -1;
+    const int64_t up = __shfl_up_sync(kFull, row, 1);
+    const bool run_start = row >= 0 && (lane == 0 ? before : up) != row;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const V vo = __shfl_down_sync(kFull, sum, o);
+        const int64_t ro = __shfl_down_sync(kFull, row, o);
+        if (lane + o < 32 && row >= 0 && ro == row) sum = add_rn(sum, vo);
+    }
+    const int64_t last = __shfl_sync(kFull, row, 31);
+    if (last >= 0) {   // warp-uniform: the window's last run may go on in the tiles behind it
+        V extra = V(0);
+        for (int u0 = base + 32;; u0 += 32) {
+            const int u = u0 + lane;
+            const bool same = u < n_tiles && (u0 == base + 32 ? beyond : carry_row[u]) == last;
+            const unsigned m = __ballot_sync(kFull, same);
+            const int n_same = m == kFull ? 32 : __ffs(~m) - 1;
+            if (lane < n_same) extra = add_rn(extra, carry_val[u]);
+            if (n_same < 32) break;
+        }
+        extra = __shfl_sync(kFull, warp_sum(extra), 0);
+        if (run_start && row == last) sum = add_rn(sum, extra);
+    }
+    if (run_start) c[row * c_stride] = add_rn(sum, c[row * c_stride]);
 }
 
 // ---------------------------------------------------------------------------
@@ -824,42 +788,27 @@ int csr_spmv_launch(cudaStream_t s, int64_t n_rows, int64_t n_cols, int64_t nnz,
     }
     if (strategy != GKOB200_CSR_MERGE_PATH && strategy != GKOB200_CSR_MERGE_PATH_PLANNED) return GKOB200_EINVAL;
     if (fused && (fu.out || fu.skip)) return GKOB200_EUNSUPPORTED;
-    const int64_t n_tiles = ceildiv(n_rows + nnz, kMpTile);
+    const int64_t n_tiles = ceildiv(n_rows + nnz, mp_tile());
     const size_t need = gkob200_csr_spmv_workspace_bytes(n_rows, nnz, nrhs, sizeof(V));
     if (!workspace || workspace_bytes < need) return GKOB200_EWORKSPACE;
     int64_t* carry_row = reinterpret_cast<int64_t*>(workspace);
     const int64_t* plan = strategy == GKOB200_CSR_MERGE_PATH_PLANNED ? carry_row + n_tiles + 1 : nullptr;
     V* carry_val = reinterpret_cast<V*>(carry_row + 2 * (n_tiles + 1) + 1);
-    static const float keep_frac = [] {
-        const char* f = getenv("GKOB200_MP_KEEP_FRAC");
-        return f ? static_cast<float>(atof(f)) : 1.0f;
+    // tiles of look-ahead for the L2 prefetch (needs 16-byte aligned arrays); GKOB200_MP_PREFETCH=0: off
+    static const int mp_prefetch = [] {
+        const char* e = getenv("GKOB200_MP_PREFETCH");
+        return e ? atoi(e) : sm_count() * 4;
     }();
-    // bulk-async staging of the tile's (col, val) ranges needs 16-byte aligned arrays
-    // (GKOB200_MP_BULK=0: register-staged loads, for A/B on the box)
-    static const bool mp_bulk = [] {
-        const char* e = getenv("GKOB200_MP_BULK");
-        return !(e && e[0] == '0');
-    }();
-    const bool bulk = mp_bulk && sizeof(I) == 4 && reinterpret_cast<uintptr_t>(values) % 16 == 0 &&
-                      reinterpret_cast<uintptr_t>(col_idxs) % 16 == 0;   // (64-bit indices: the staging would not fit 48 KB)
-    const int mp_pf = sm_count() * 4;
-#define GKOB200_MP(ADV, BULK)                                                                              \
-    csr_spmv_merge<V, I, ADV, BULK><<<static_cast<unsigned>(n_tiles), kMpThreads, 0, s>>>(                 \
-        n_rows, nnz, row_ptrs, col_idxs, values, b, b_stride, alpha, beta, c, c_stride, carry_row, carry_val, \
-        plan, keep_frac, mp_pf)
-    if (bulk) {
-        if constexpr (sizeof(I) == 4) {
-            if (adv) GKOB200_MP(true, true);
-            else GKOB200_MP(false, true);
-        }
-    } else if (adv) {
-        GKOB200_MP(true, false);
-    } else {
-        GKOB200_MP(false, false);
-    }
+    const int pf = (reinterpret_cast<uintptr_t>(values) % 16 == 0 && reinterpret_cast<uintptr_t>(col_idxs) % 16 == 0) ? mp_prefetch : 0;
+#define GKOB200_MP(ADV, T)                                                                                 \
+    csr_spmv_merge<V, I, ADV, T><<<static_cast<unsigned>(n_tiles), T, 0, s>>>(                             \
+        n_rows, nnz, row_ptrs, col_idxs, values, b, b_stride, alpha, beta, c, c_stride, carry_row, carry_val, plan, pf)
+    if (mp_threads() == 64) { if (adv) GKOB200_MP(true, 64); else GKOB200_MP(false, 64); }
+    else if (mp_threads() == 128) { if (adv) GKOB200_MP(true, 128); else GKOB200_MP(false, 128); }
+    else { if (adv) GKOB200_MP(true, 256); else GKOB200_MP(false, 256); }
 #undef GKOB200_MP
     GKOB200_CHECK_LAUNCH();
-    csr_spmv_merge_fixup<V><<<static_cast<unsigned>(ceildiv(n_tiles, 8)), 256, 0, s>>>(
+    csr_spmv_merge_fixup<V><<<static_cast<unsigned>(ceildiv(n_tiles, 256)), 256, 0, s>>>(
         static_cast<int>(n_tiles), carry_row, carry_val, n_rows, c, c_stride);
     GKOB200_CHECK_LAUNCH();
     return 0;
@@ -887,10 +836,10 @@ static int merge_plan_impl(void* stream, int64_t n_rows, int64_t nnz, const I* r
     if (n_rows == 0) return 0;
     if (!row_ptrs) return GKOB200_EINVAL;
     if (!workspace || workspace_bytes < gkob200_csr_spmv_workspace_bytes(n_rows, nnz, 1, 8)) return GKOB200_EWORKSPACE;
-    const int64_t n_tiles = ceildiv(n_rows + nnz, kMpTile);
+    const int64_t n_tiles = ceildiv(n_rows + nnz, mp_tile());
     int64_t* plan = reinterpret_cast<int64_t*>(workspace) + n_tiles + 1;
     csr_merge_plan<I><<<static_cast<unsigned>(ceildiv(n_tiles + 1, 256)), 256, 0, as_stream(stream)>>>(n_tiles, n_rows, nnz,
-                                                                                                   row_ptrs, plan);
+                                                                                                   row_ptrs, plan, mp_tile());
     GKOB200_CHECK_LAUNCH();
     return 0;
 }
@@ -900,7 +849,7 @@ size_t gkob200_csr_spmv_workspace_bytes(int64_t n_rows, int64_t nnz, int64_t nrh
 {
     (void)nrhs;
     // [carry_row: n_tiles+1][plan (tile split rows): n_tiles+2][carry_val: n_tiles+1]
-    const int64_t n_tiles = ceildiv(n_rows + nnz, kMpTile) + 2;
+    const int64_t n_tiles = ceildiv(n_rows + nnz, mp_tile()) + 2;
     return static_cast<size_t>(n_tiles) * (2 * sizeof(int64_t) + static_cast<size_t>(value_bytes)) + 64;
 }
 

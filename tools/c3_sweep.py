@@ -6,7 +6,7 @@ import torch
 from __graft_entry__ import load_package
 gko = load_package()
 exec_ = gko.CudaExecutor.create(0)
-for n in (1_000_000, 2_000_000, 4_000_000, 7_000_000, 10_000_000):
+for n in [int(a) for a in sys.argv[1:]] or (1_000_000, 2_000_000, 4_000_000, 7_000_000, 10_000_000):
     rp, ci, va = gko.gen.powerlaw_csr(n)
     A = gko.matrix.Csr.from_arrays(exec_, (n, n), rp, ci, va)
     x = gko.matrix.Dense.create(exec_, (n, 1)); y = gko.matrix.Dense.create(exec_, (n, 1))
