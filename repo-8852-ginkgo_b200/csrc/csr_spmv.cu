@@ -378,19 +378,9 @@ __global__ void __launch_bounds__(kRowsPerCta, rowblock_min_ctas(kBatch, sizeof(
 // ---------------------------------------------------------------------------
 // merge-path kernel (single right-hand side)
 // ---------------------------------------------------------------------------
-constexpr int kMpThreads = 256;
+constexpr int kMpThreads = 128;
 constexpr int kMpItems = 9;                            // merge items per thread (odd: conflict-free)
 constexpr int kMpTile = kMpThreads * kMpItems;         // merge items per CTA
-static int mp_threads()
-{
-    static const int t = [] {
-        const char* e = getenv("GKOB200_MP_THREADS");
-        const int v = e ? atoi(e) : 128;
-        return v == 64 || v == 256 ? v : 128;
-    }();
-    return t;
-}
-static int mp_tile() { return mp_threads() * kMpItems; }
 
 // Merge-path diagonal search: how many of the first `diag` merge items are row
 // ends.  List A = row end offsets row_ptrs[1..n], list B = 0..nnz-1; a row end is
@@ -426,20 +416,23 @@ __device__ __forceinline__ int64_t merge_path_search(int64_t diag, const P row_e
 // barrier.  History (profiles/r02_merge_source_phases.txt): the previous kernel flagged row
 // heads per entry, reduced kMpItems consecutive products per thread and stitched the pieces in
 // thread order — 8 barriers per tile, 37 % of all warp time in the stitch and the barrier
-// behind it; 833 us on the 10 M-row power-law matrix against 721 us for this one.
-// 4 resident CTAs (64 registers) is the measured optimum at 10 M rows: 3 CTAs 785 us, 5 CTAs
-// (48 registers) 794 us, 6 CTAs (40 registers, spills) 1128 us.
+// behind it; 833 us on the 10 M-row power-law matrix.
+// Measured at 10 M rows (tools/c3_sweep.py): 128 threads x 8 resident CTAs (58 registers) 659 us;
+// 10 CTAs (48 registers) 770 us, 12 CTAs (40 registers, spills) 1141 us; 256-thread tiles 4 % slower;
+// look-ahead L2 prefetch + streaming stores of c: 685 -> 676 us (8 % at 4-7 M rows); the
+// lane-per-tile fix-up: 676 -> 662 us.  A kernel that ONLY streams (col, val) and gathers b[col]
+// (tools/probe/gather_probe.cu) takes 465 us on this matrix: that, not the algorithmic-byte
+// roofline, is the bound a CSR SpMV can approach here.
 constexpr int kMpLongRow = 48;
 
-template <typename V, typename I, bool Advanced, int kMpThreads>
-__global__ void __launch_bounds__(kMpThreads, 1024 / kMpThreads)
+template <typename V, typename I, bool Advanced>
+__global__ void __launch_bounds__(kMpThreads, 8)
     csr_spmv_merge(int64_t n_rows, int64_t nnz, const I* __restrict__ row_ptrs, const I* __restrict__ col_idxs,
                    const V* __restrict__ values, const V* __restrict__ b, int64_t b_stride,
                    const V* __restrict__ alpha_p, const V* __restrict__ beta_p, V* __restrict__ c,
                    int64_t c_stride, int64_t* __restrict__ carry_row, V* __restrict__ carry_val,
                    const int64_t* __restrict__ plan, int prefetch_tiles)
 {
-    constexpr int kMpTile = kMpThreads * kMpItems;
     __shared__ __align__(16) V s_prod[kMpTile];
     __shared__ int s_start[kMpTile + 2];   // [r]: first product of tile row r; [n_tile_rows + 1] = n_tile_nnz
     __shared__ int64_t s_range[2];
@@ -788,7 +781,7 @@ int csr_spmv_launch(cudaStream_t s, int64_t n_rows, int64_t n_cols, int64_t nnz,
     }
     if (strategy != GKOB200_CSR_MERGE_PATH && strategy != GKOB200_CSR_MERGE_PATH_PLANNED) return GKOB200_EINVAL;
     if (fused && (fu.out || fu.skip)) return GKOB200_EUNSUPPORTED;
-    const int64_t n_tiles = ceildiv(n_rows + nnz, mp_tile());
+    const int64_t n_tiles = ceildiv(n_rows + nnz, kMpTile);
     const size_t need = gkob200_csr_spmv_workspace_bytes(n_rows, nnz, nrhs, sizeof(V));
     if (!workspace || workspace_bytes < need) return GKOB200_EWORKSPACE;
     int64_t* carry_row = reinterpret_cast<int64_t*>(workspace);
@@ -800,12 +793,11 @@ int csr_spmv_launch(cudaStream_t s, int64_t n_rows, int64_t n_cols, int64_t nnz,
         return e ? atoi(e) : sm_count() * 4;
     }();
     const int pf = (reinterpret_cast<uintptr_t>(values) % 16 == 0 && reinterpret_cast<uintptr_t>(col_idxs) % 16 == 0) ? mp_prefetch : 0;
-#define GKOB200_MP(ADV, T)                                                                                 \
-    csr_spmv_merge<V, I, ADV, T><<<static_cast<unsigned>(n_tiles), T, 0, s>>>(                             \
+#define GKOB200_MP(ADV)                                                                                    \
+    csr_spmv_merge<V, I, ADV><<<static_cast<unsigned>(n_tiles), kMpThreads, 0, s>>>(                       \
         n_rows, nnz, row_ptrs, col_idxs, values, b, b_stride, alpha, beta, c, c_stride, carry_row, carry_val, plan, pf)
-    if (mp_threads() == 64) { if (adv) GKOB200_MP(true, 64); else GKOB200_MP(false, 64); }
-    else if (mp_threads() == 128) { if (adv) GKOB200_MP(true, 128); else GKOB200_MP(false, 128); }
-    else { if (adv) GKOB200_MP(true, 256); else GKOB200_MP(false, 256); }
+    if (adv) GKOB200_MP(true);
+    else GKOB200_MP(false);
 #undef GKOB200_MP
     GKOB200_CHECK_LAUNCH();
     csr_spmv_merge_fixup<V><<<static_cast<unsigned>(ceildiv(n_tiles, 256)), 256, 0, s>>>(
@@ -836,10 +828,10 @@ static int merge_plan_impl(void* stream, int64_t n_rows, int64_t nnz, const I* r
     if (n_rows == 0) return 0;
     if (!row_ptrs) return GKOB200_EINVAL;
     if (!workspace || workspace_bytes < gkob200_csr_spmv_workspace_bytes(n_rows, nnz, 1, 8)) return GKOB200_EWORKSPACE;
-    const int64_t n_tiles = ceildiv(n_rows + nnz, mp_tile());
+    const int64_t n_tiles = ceildiv(n_rows + nnz, kMpTile);
     int64_t* plan = reinterpret_cast<int64_t*>(workspace) + n_tiles + 1;
     csr_merge_plan<I><<<static_cast<unsigned>(ceildiv(n_tiles + 1, 256)), 256, 0, as_stream(stream)>>>(n_tiles, n_rows, nnz,
-                                                                                                   row_ptrs, plan, mp_tile());
+                                                                                                   row_ptrs, plan, kMpTile);
     GKOB200_CHECK_LAUNCH();
     return 0;
 }
@@ -849,7 +841,7 @@ size_t gkob200_csr_spmv_workspace_bytes(int64_t n_rows, int64_t nnz, int64_t nrh
 {
     (void)nrhs;
     // [carry_row: n_tiles+1][plan (tile split rows): n_tiles+2][carry_val: n_tiles+1]
-    const int64_t n_tiles = ceildiv(n_rows + nnz, mp_tile()) + 2;
+    const int64_t n_tiles = ceildiv(n_rows + nnz, kMpTile) + 2;
     return static_cast<size_t>(n_tiles) * (2 * sizeof(int64_t) + static_cast<size_t>(value_bytes)) + 64;
 }
 
