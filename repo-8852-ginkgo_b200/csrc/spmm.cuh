@@ -194,6 +194,70 @@ __device__ __forceinline__ void entry_step(V (&acc)[kTileRows], const I* s_col, 
     }
 }
 
+// ---- several columns per lane ---------------------------------------------------------------
+// With kVec = 16 / sizeof(V) columns per lane a row of b with 32 columns is covered by 32 / kVec
+// lanes, and the warp's kVec lane groups work on different rows of the tile at the same time:
+// per staged slot of the 8-row tile a lane issues kTileRows / kVec 128-bit loads instead of 8
+// 32-bit ones, 2 instead of 4 shared-memory loads and kTileRows / kVec instead of 8 address
+// computations — 2.75 instead of 4.5 warp instructions per stored entry for fp32, the rounded
+// multiplies and adds (2 per entry, bit parity forbids the FMA) being the floor.  Per (row, column)
+// the operations and their order are unchanged: results stay bit-identical.
+template <typename V>
+struct alignas(16) Vec16 {
+    V e[16 / sizeof(V)];
+};
+template <typename V>
+__device__ __forceinline__ Vec16<V> ldg16(const V* p)
+{
+    union {
+        uint4 raw;
+        Vec16<V> v;
+    } u;
+    u.raw = __ldg(reinterpret_cast<const uint4*>(p));
+    return u.v;
+}
+// kN consecutive shared-memory elements, kN * sizeof(T) in {8, 16, 32}, aligned to min(that, 16)
+template <int kN, typename T>
+__device__ __forceinline__ void lds_small(const T* p, T (&out)[kN])
+{
+    constexpr int bytes = kN * sizeof(T);
+    static_assert(bytes == 8 || bytes % 16 == 0, "unsupported group size");
+    if constexpr (bytes == 8) {
+        union {
+            uint2 raw;
+            T t[kN];
+        } u;
+        u.raw = *reinterpret_cast<const uint2*>(p);
+#pragma unroll
+        for (int i = 0; i < kN; ++i) out[i] = u.t[i];
+    } else {
+        lds_vec(p, out);
+    }
+}
+
+template <bool Checked, bool Advanced, int kRows, typename V, typename I>
+__device__ __forceinline__ void entry_step_vec(V (&acc)[kRows][16 / sizeof(V)], const I* s_col, const V* s_val,
+                                               const V* b_j, uint32_t b_pitch, V alpha)
+{
+    constexpr int kVec = 16 / sizeof(V);
+    I col[kRows];
+    V v[kRows];
+    Vec16<V> xv[kRows];
+    lds_small(s_col, col);
+    lds_small(s_val, v);
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) xv[r] = ldg16(b_row(b_j, Checked && col[r] < I(0) ? I(0) : col[r], b_pitch));
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+        const V av = Advanced ? mul_rn(alpha, v[r]) : v[r];
+#pragma unroll
+        for (int e = 0; e < kVec; ++e) {
+            const V p = mul_rn(av, xv[r].e[e]);
+            acc[r][e] = (!Checked || col[r] >= I(0)) ? add_rn(acc[r][e], p) : acc[r][e];
+        }
+    }
+}
+
 // ---- lattice-aware tile order ------------------------------------------------------------
 // Every stored entry needs one full row of b; a CTA whose warps own CONSECUTIVE row tiles can
 // only reuse fetched rows along the fastest grid direction (at best 9 of the 27 rows a 27-pt
@@ -278,7 +342,7 @@ __device__ __forceinline__ int64_t lattice_tile(const Lattice& L, int64_t pass, 
     return (q * 16 + wid) * L.line_tiles + xt;
 }
 
-template <typename V, typename I, typename Stager, typename C, bool Advanced>
+template <typename V, typename I, typename Stager, typename C, bool Advanced, bool Vector>
 __global__ void __launch_bounds__(C::kWarps * 32, C::kMinCtas)
     spmm_tiles(int64_t n_rows, Stager st, const V* __restrict__ b, uint32_t b_pitch, int64_t nrhs,
                const V* __restrict__ alpha_p, const V* __restrict__ beta_p, V* __restrict__ c,
@@ -322,6 +386,47 @@ __global__ void __launch_bounds__(C::kWarps * 32, C::kMinCtas)
             const bool clean = st.stage(s_col, s_val, lane);
             __syncwarp();
             const int n_k = static_cast<int>(st.max_len);
+            if constexpr (Vector) {
+                constexpr int kVec = 16 / sizeof(V), kLanesPerRow = 32 / kVec, kRows = kTileRows / kVec;
+                static_assert(kTileRows % kVec == 0, "tile rows must split over the lane groups");
+                const int g = lane / kLanesPerRow;          // lane group: rows g*kRows .. of the tile
+                const int jl_lane = (lane % kLanesPerRow) * kVec;
+                for (int64_t j0 = 0; j0 < nrhs; j0 += 32) {
+                    const bool jl = j0 + jl_lane < nrhs;    // (nrhs is a multiple of kVec)
+                    const int64_t j = jl ? j0 + jl_lane : 0;
+                    const V* b_j = b + j;
+                    V acc[kRows][kVec];
+#pragma unroll
+                    for (int r = 0; r < kRows; ++r) {
+                        const int tr = g * kRows + r;
+                        Vec16<V> c0;
+                        if (Advanced && tr < nr) c0 = *reinterpret_cast<const Vec16<V>*>(c + (row0 + tr) * c_stride + j);
+#pragma unroll
+                        for (int e = 0; e < kVec; ++e) acc[r][e] = (Advanced && tr < nr) ? mul_rn(c0.e[e], beta) : V(0);
+                    }
+                    const I* g_col = s_col + g * kRows;
+                    const V* g_val = s_val + g * kRows;
+                    if (clean) {
+#pragma unroll 2
+                        for (int k = 0; k < n_k; ++k)
+                            entry_step_vec<false, Advanced>(acc, g_col + k * kTileRows, g_val + k * kTileRows, b_j, b_pitch, alpha);
+                    } else {
+                        for (int k = 0; k < n_k; ++k)
+                            entry_step_vec<true, Advanced>(acc, g_col + k * kTileRows, g_val + k * kTileRows, b_j, b_pitch, alpha);
+                    }
+#pragma unroll
+                    for (int r = 0; r < kRows; ++r) {
+                        const int tr = g * kRows + r;
+                        if (jl && tr < nr) {
+                            Vec16<V> out;
+#pragma unroll
+                            for (int e = 0; e < kVec; ++e) out.e[e] = acc[r][e];
+                            *reinterpret_cast<Vec16<V>*>(c + (row0 + tr) * c_stride + j) = out;
+                        }
+                    }
+                }
+                continue;
+            }
             for (int64_t j0 = 0; j0 < nrhs; j0 += 32) {
                 const bool jl = j0 + lane < nrhs;
                 const int64_t j = jl ? j0 + lane : 0;
@@ -410,15 +515,27 @@ int launch_cfg(cudaStream_t s, int64_t n_rows, const Stager& st, const V* b, int
     }();
     // leave the rest of the 256 KB to L1: the kernel lives on L1 hits for b
     const int carve = static_cast<int>((smem + 1024) * C::kMinCtas * 100 / (228 * 1024)) + 1;
-    if (alpha) {
-        const cudaError_t attr = prepare<spmm_tiles<V, I, Stager, C, true>>(smem, carve);
-        if (attr != cudaSuccess) return static_cast<int>(attr);
-        spmm_tiles<V, I, Stager, C, true><<<grid, kWarps * 32, smem, s>>>(n_rows, st, b, pitch, nrhs, alpha, beta, c, c_stride, passes, lattice_mode);
-    } else {
-        const cudaError_t attr = prepare<spmm_tiles<V, I, Stager, C, false>>(smem, carve);
-        if (attr != cudaSuccess) return static_cast<int>(attr);
-        spmm_tiles<V, I, Stager, C, false><<<grid, kWarps * 32, smem, s>>>(n_rows, st, b, pitch, nrhs, alpha, beta, c, c_stride, passes, lattice_mode);
+    // several columns per lane need 16-byte aligned rows of b and c (GKOB200_SPMM_VECTOR=0: one column
+    // per lane, for A/B on the box)
+    static const bool vector_ok = [] {
+        const char* e = getenv("GKOB200_SPMM_VECTOR");
+        return !(e && e[0] == '0');
+    }();
+    constexpr int kVec = 16 / sizeof(V);
+    const bool vec = vector_ok && nrhs % kVec == 0 && reinterpret_cast<uintptr_t>(b) % 16 == 0 &&
+                     reinterpret_cast<uintptr_t>(c) % 16 == 0 && b_stride % kVec == 0 && c_stride % kVec == 0;
+#define GKOB200_SPMM(ADV, VEC)                                                                             \
+    {                                                                                                      \
+        const cudaError_t attr = prepare<spmm_tiles<V, I, Stager, C, ADV, VEC>>(smem, carve);              \
+        if (attr != cudaSuccess) return static_cast<int>(attr);                                            \
+        spmm_tiles<V, I, Stager, C, ADV, VEC><<<grid, kWarps * 32, smem, s>>>(n_rows, st, b, pitch, nrhs, alpha, beta, c, \
+                                                                               c_stride, passes, lattice_mode);  \
     }
+    if (alpha && vec) GKOB200_SPMM(true, true)
+    else if (alpha) GKOB200_SPMM(true, false)
+    else if (vec) GKOB200_SPMM(false, true)
+    else GKOB200_SPMM(false, false)
+#undef GKOB200_SPMM
     GKOB200_CHECK_LAUNCH();
     return 0;
 }
