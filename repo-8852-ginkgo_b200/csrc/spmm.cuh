@@ -330,17 +330,40 @@ __device__ __forceinline__ Lattice detect_lattice(const int64_t* sample_cols, in
     return L;
 }
 
-// logical (pass, warp) -> row tile
-__device__ __forceinline__ int64_t lattice_tile(const Lattice& L, int64_t pass, int wid)
-{
-    const int64_t xt = pass % L.line_tiles;
-    const int64_t q = pass / L.line_tiles;
-    if (L.planes > 1) {
-        const int64_t yb = q % (L.lines / 4), zb = q / (L.lines / 4);
-        return ((zb * 4 + (wid >> 2)) * L.lines + yb * 4 + (wid & 3)) * L.line_tiles + xt;
+// logical (pass, warp) -> row tile.  The passes of a CTA are consecutive, so the position is
+// split into (along the line, line block, plane block) once per CTA and then advanced like an
+// odometer: 64-bit divisions per pass and warp were a quarter of the instructions outside the
+// inner loop.
+struct LatticeCursor {
+    int64_t xt, yb, zb;   // tile along the line, line block (of 4, or of 16 in 2-D), plane block (of 4)
+    __device__ __forceinline__ void seek(const Lattice& L, int64_t pass)
+    {
+        xt = pass % L.line_tiles;
+        const int64_t q = pass / L.line_tiles;
+        if (L.planes > 1) {
+            yb = q % (L.lines / 4);
+            zb = q / (L.lines / 4);
+        } else {
+            yb = q;
+            zb = 0;
+        }
     }
-    return (q * 16 + wid) * L.line_tiles + xt;
-}
+    __device__ __forceinline__ void advance(const Lattice& L)
+    {
+        if (++xt < L.line_tiles) return;
+        xt = 0;
+        ++yb;
+        if (L.planes > 1 && yb == L.lines / 4) {
+            yb = 0;
+            ++zb;
+        }
+    }
+    __device__ __forceinline__ int64_t tile(const Lattice& L, int wid) const
+    {
+        if (L.planes > 1) return ((zb * 4 + (wid >> 2)) * L.lines + yb * 4 + (wid & 3)) * L.line_tiles + xt;
+        return (yb * 16 + wid) * L.line_tiles + xt;
+    }
+};
 
 template <typename V, typename I, typename Stager, typename C, bool Advanced, bool Vector>
 __global__ void __launch_bounds__(C::kWarps * 32, C::kMinCtas)
@@ -369,12 +392,14 @@ __global__ void __launch_bounds__(C::kWarps * 32, C::kMinCtas)
         __syncthreads();
     }
     const Lattice lat = lattice_mode ? s_lattice : Lattice{0, 0, 1};
+    LatticeCursor cur{0, 0, 0};
+    if (lat.line_tiles > 0) cur.seek(lat, static_cast<int64_t>(blockIdx.x) * passes);
     for (int pass = 0; pass < passes; ++pass) {
         int64_t tile = cta_tile0 + static_cast<int64_t>(pass) * kWarps + wid;
         if (lat.line_tiles > 0) {
-            const int64_t p = static_cast<int64_t>(blockIdx.x) * passes + pass;
-            if (p * kWarps >= n_tiles) break;
-            tile = lattice_tile(lat, p, wid);
+            if ((static_cast<int64_t>(blockIdx.x) * passes + pass) * kWarps >= n_tiles) break;
+            tile = cur.tile(lat, wid);
+            cur.advance(lat);
         }
         if (tile >= n_tiles) break;
         const int64_t row0 = tile * kTileRows;
