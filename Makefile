@@ -22,9 +22,14 @@ bench-reference: build
 bench-configs: build
 	$(PY) tools/bench_configs.py
 
+# stream (col, val) + gather only: the bound of a CSR SpMV on the power-law matrix
+gather-probe: build
+	$(PY) tools/gather_probe.py 10000000
+
 clean:
 	$(MAKE) -C repo-8852-ginkgo_b200/csrc clean
 	$(MAKE) -C oracle clean
 	$(MAKE) -C shim clean
+	$(MAKE) -C tools/probe clean
 
-.PHONY: build test-cpu test-gpu smoke bench bench-reference bench-configs clean
+.PHONY: build test-cpu test-gpu smoke bench bench-reference bench-configs gather-probe clean

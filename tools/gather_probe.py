@@ -6,7 +6,10 @@ sys.path.insert(0, ROOT)
 import torch
 from __graft_entry__ import load_package
 gko = load_package()
-lib = C.CDLL(os.path.join(ROOT, "tools", "probe", "libgather_probe.so"))
+_so = os.path.join(ROOT, "tools", "probe", "libgather_probe.so")
+if not os.path.exists(_so):
+    sys.exit("tools/probe/libgather_probe.so is missing: run `make -C tools/probe` (or __graft_entry__.build())")
+lib = C.CDLL(_so)
 lib.gather_probe.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 exec_ = gko.CudaExecutor.create(0)
 dev = exec_.device
