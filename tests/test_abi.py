@@ -47,3 +47,21 @@ def test_pick_strategy_is_pure_host(gko):
     assert gko.lib.gkob200_csr_pick_strategy(8_000_000, 213_847_192, 27, 27 * 128) == 0
     assert gko.lib.gkob200_csr_pick_strategy(10_000_000, 100_000_000, 100_000, 150_000) == 1
     assert gko.lib.gkob200_csr_pick_strategy(0, 0, 0, 0) == 0
+
+
+def test_merge_path_workspace_covers_carries_and_plan(gko):
+    # layout (csr_spmv.cu): [carry_row: n_tiles + 1][plan: n_tiles + 2][carry_val: n_tiles + 1], one tile =
+    # 128 threads x 9 merge items; the size is a pure host function, monotone in rows + entries
+    import ctypes as C
+    f = gko.lib.gkob200_csr_spmv_workspace_bytes
+    f.restype = C.c_size_t
+    tile = 128 * 9
+    prev = 0
+    for n_rows, nnz in [(1, 0), (1, 50), (5000, 20_000), (10_000_000, 95_363_401)]:
+        n_tiles = -(-(n_rows + nnz) // tile)
+        for vb in (4, 8):
+            got = f(C.c_int64(n_rows), C.c_int64(nnz), C.c_int64(1), C.c_int(vb))
+            assert got >= (n_tiles + 1) * 8 + (n_tiles + 2) * 8 + (n_tiles + 1) * vb
+            assert got <= (n_tiles + 3) * (16 + vb) + 4096
+        assert got >= prev
+        prev = got
