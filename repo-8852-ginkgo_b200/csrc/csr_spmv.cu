@@ -16,13 +16,14 @@
 //    left to right with a rounded product and a rounded add: the result is
 //    bit-identical to the reference executor.
 //
-//  * merge-path: rows+nnz are split evenly over CTAs and again over threads
-//    (Merrill & Garland), products are formed during the coalesced staging
-//    pass, each thread consumes a fixed number of merge items, partial rows are
-//    stitched with a block-wide segmented scan and per-CTA carries are applied by
-//    a small deterministic fix-up kernel (no atomics, no zero-fill pass, no
-//    allocation — the reference's merge_path allocates two arrays per call and
-//    its load_balance kernel needs a fill pass plus fp64 atomics).
+//  * merge-path: rows+nnz are split evenly over CTAs (Merrill & Garland's merge
+//    path, split rows planned once per matrix), products are formed during the
+//    coalesced staging pass, one thread per tile row sums that row's products in
+//    storage order behind a single barrier (long rows: the whole warp), and the
+//    per-CTA carries of rows that cross tiles are applied by a small
+//    deterministic fix-up kernel (no atomics, no zero-fill pass, no allocation —
+//    the reference's merge_path allocates two arrays per call and its
+//    load_balance kernel needs a fill pass plus fp64 atomics).
 //
 // Algorithmic bytes per launch: nnz*(V+I) + (n+1)*I + n_cols*k*V + n*k*V.
 #include <cstdlib>
